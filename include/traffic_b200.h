@@ -1,0 +1,134 @@
+/*
+ * traffic_b200 - C ABI of the B200-native per-timestep vehicle update.
+ *
+ * This is the drop-in boundary for the hot path of donjpierce/traffic: the loop body of
+ * test/profile_cars_update.py:28-34, i.e. Cars.update(dt, lights) (cars.py:61-95) and
+ * TrafficLights.update(dt) (cars.py:123-133).  The reference has no FFI layer of its own (pure Python); the
+ * binding a maintainer adds is a ctypes stub inside cars.py (shown in INTEGRATION.md), and the entry points below
+ * are exactly what that stub binds.  Plain pointers and sizes only; no torch types.
+ *
+ * Memory model: one simulation = one opaque tb2_sim that owns a single device arena.  The arena is either
+ * supplied by the host (a torch uint8 tensor's data_ptr, so PyTorch's caching allocator owns the memory and
+ * re-creating a Cars object per episode is cheap - environment.py:50-51,85) or cudaMalloc'ed by the library when
+ * NULL is passed.  Uploads/downloads accept host OR device pointers (cudaMemcpyDefault).  All work is issued on
+ * the caller's stream (a cudaStream_t passed as void*); nothing synchronises unless stated.
+ *
+ * Every function returns 0 on success and a non-zero tb2_status on failure; tb2_last_error() gives the message.
+ * There is no CPU fallback: without a CUDA device tb2_create fails.
+ */
+#ifndef TRAFFIC_B200_H
+#define TRAFFIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB2_ABI_VERSION 1
+
+/* order of the two reference calls inside one step */
+#define TB2_ORDER_CARS_LIGHTS 0 /* test/profile_cars_update.py:29-34 */
+#define TB2_ORDER_LIGHTS_CARS 1 /* animate.py:63-64, environment.py:167-168 */
+
+/* arithmetic modes */
+#define TB2_F64 0 /* reference arithmetic (numpy float64 evaluation order) - parity mode            */
+#define TB2_F32 1 /* throughput mode: fp32 state in local-origin coordinates, tolerances from absolute */
+
+typedef enum tb2_status {
+    TB2_OK = 0,
+    TB2_ERR_INVALID = 1,   /* bad argument / size mismatch */
+    TB2_ERR_CUDA = 2,      /* a CUDA runtime call failed (message has the cudaError string) */
+    TB2_ERR_NO_DEVICE = 3, /* no CUDA device: the library has no CPU path */
+    TB2_ERR_STATE = 4      /* call sequence error (e.g. step before prepare) */
+} tb2_status;
+
+/* Fields of the device-resident structure of arrays.  Element types are for TB2_F64 / TB2_F32. */
+typedef enum tb2_field {
+    TB2_POS = 0,          /* [N][2] f64 | f32 (f32: relative to origin_x/origin_y)  cars 'x','y'          */
+    TB2_VEL = 1,          /* [N][2] f64 | f32                                       cars 'vx','vy'        */
+    TB2_ROUTE_TIME = 2,   /* [N]    f64 | f32                                       cars 'route-time'     */
+    TB2_CURSOR = 3,       /* [N]    i32  absolute index of the path head in PATH_XY (popped points = cursor - start) */
+    TB2_PATH_END = 4,     /* [N]    i32  one past the car's last polyline point                           */
+    TB2_PATH_EFF_END = 5, /* [N]    i32  has_path <=> cursor < eff_end (navigation.py:37-39 `.any()` rule) */
+    TB2_PATH_XY = 6,      /* [P][2] f64 | f32  all polylines back to back (xpath/ypath)                   */
+    TB2_DEST_XY = 7,      /* [N][2] f64 | f32  destination node position (navigation.py:84,89)            */
+    TB2_D_NODE = 8,       /* [N]    f64 | f32  'distance-to-node'                                         */
+    TB2_D_CAR = 9,        /* [N]    f64 | f32  'distance-to-car', 0 encodes False                         */
+    TB2_D_LIGHT = 10,     /* [N]    f64 | f32  'distance-to-red-light', +0 = False, -0 = None             */
+    TB2_CELL = 11,        /* [N]    i32  ybin*(nbx+1)+xbin of the start-of-step position ('xbin','ybin')   */
+    TB2_LEADER = 12,      /* [N]    i32  index of the car accepted as obstacle, -1 if none                */
+    TB2_LIGHT_XY = 13,    /* [L][2] f64 | f32                                                             */
+    TB2_SWITCH_TIME = 14, /* [L]    f64 (always f64: cars.py:131 is a round-off artefact, Appendix B-6)   */
+    TB2_FACE_PTR = 15,    /* [L+1]  i32                                                                   */
+    TB2_FACE_VEC = 16,    /* [F][2] f64 | f32  'out-xvectors','out-yvectors'                              */
+    TB2_FACE_GO = 17,     /* [F]    u8   'go-values'                                                      */
+    TB2_CELL_LIGHT_PTR = 18, /* [C+1] i32  static cell -> lights CSR (lights in DataFrame order)           */
+    TB2_CELL_LIGHT_IDX = 19, /* [LC]  i32                                                                  */
+    TB2_LIGHTS_TIME = 20, /* [1]    f64  TrafficLights.time_elapsed (cars.py:117,130)                     */
+    TB2_FIELD_COUNT = 21
+} tb2_field;
+
+typedef struct tb2_config {
+    int32_t abi_version; /* must be TB2_ABI_VERSION */
+    int32_t precision;   /* TB2_F64 | TB2_F32 */
+    int32_t n_cars, n_lights, n_faces;
+    int32_t n_cell_lights;     /* length of TB2_CELL_LIGHT_IDX */
+    int64_t n_path_points;     /* P */
+    /* bins: models.determine_bins (models.py:7-19).  nb = len(np.arange(lo, hi, 200)); e0,e1 = first two edges,
+     * ed = e1 - e0 (numpy's arange fill rule, so that edge k = e0 + k*ed bit-for-bit). */
+    int32_t nbx, nby;
+    double ex0, ex1, exd;
+    double ey0, ey1, eyd;
+    /* simulation.py:13-16 */
+    double speed_limit, stop_distance, free_distance, default_acceleration;
+    /* TB2_F32 only: positions are stored as (x - origin_x, y - origin_y) */
+    double origin_x, origin_y;
+    int32_t write_aux;   /* 1: write TB2_LEADER / TB2_CELL / distances every step (parity + facade); 0: skip LEADER */
+    int32_t reserved;
+} tb2_config;
+
+typedef struct tb2_sim tb2_sim;
+
+int tb2_abi_version(void);
+const char* tb2_last_error(void);
+
+/* bytes of device memory a simulation with this config needs (the host may allocate it, e.g. with torch) */
+size_t tb2_arena_bytes(const tb2_config* cfg);
+
+/* replaces Cars.__init__ + TrafficLights.__init__ (cars.py:23-41, 110-121): allocates/carves device state.
+ * arena_dev may be NULL (library allocates). */
+int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_sim** out);
+int tb2_destroy(tb2_sim* sim);
+
+/* element count / element size / current device pointer of a field (POS flips buffers every step) */
+int tb2_field_info(const tb2_sim* sim, int field, size_t* n_elems, size_t* elem_bytes);
+void* tb2_field_ptr(const tb2_sim* sim, int field);
+
+/* src/dst: host or device memory; bytes must equal n_elems*elem_bytes */
+int tb2_upload(tb2_sim* sim, int field, const void* src, size_t bytes, void* stream);
+int tb2_download(const tb2_sim* sim, int field, void* dst, size_t bytes, void* stream);
+
+/* (re)build the cell -> two-smallest-car-index table from the current positions; call after uploading POS
+ * (replaces the bin assignment at the end of the reference initialisers, simulation.py:246-250) */
+int tb2_prepare(tb2_sim* sim, void* stream);
+
+/* n_steps of { Cars.update(dt, lights.state) ; TrafficLights.update(dt) } in the given order (cars.py:61-95,
+ * 123-133).  Asynchronous on `stream`. */
+int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stream);
+
+/* End-to-end variant with HOST buffers (what Cars.update does for a caller that passes the lights DataFrame and
+ * reads positions back, animate.py:63-69): optional H2D of the face states, n_steps, D2H of positions (frame_xy,
+ * [N][2] in the sim's precision) and, when non-NULL, the face states.  Synchronises `stream` before returning. */
+int tb2_step_host(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
+                  void* frame_xy_out, uint8_t* face_go_out, void* stream);
+
+/* number of kernel launches issued by this sim so far (bench.py's gpu_launches) */
+int64_t tb2_launch_count(const tb2_sim* sim);
+int64_t tb2_step_count(const tb2_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAFFIC_B200_H */

@@ -1,0 +1,341 @@
+// C ABI of libtraffic_b200.so (declared in include/traffic_b200.h): arena carving, uploads/downloads, and the
+// launch sequence of a simulation step.  Host-side only; the kernels live in step_f64.cu / step_f32.cu.
+#include "../../include/traffic_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "step_f64.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return TB2_ERR_CUDA;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+constexpr size_t kAlign = 256;
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+// internal buffer ids (superset of tb2_field: ping-pong partners and the cell tables)
+enum Buf {
+    B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
+    B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL0, B_CELL1, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
+    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_COUNT
+};
+
+struct Layout {
+    size_t off[B_COUNT];
+    size_t bytes[B_COUNT];
+    size_t total;
+};
+
+bool config_ok(const tb2_config* c, std::string* why) {
+    if (!c) { *why = "null config"; return false; }
+    if (c->abi_version != TB2_ABI_VERSION) { *why = "abi_version mismatch"; return false; }
+    if (c->precision != TB2_F64) { *why = "unsupported precision (only TB2_F64 is built into this library)"; return false; }
+    if (c->n_cars < 0 || c->n_lights < 0 || c->n_faces < 0 || c->n_cell_lights < 0 || c->n_path_points < 0) {
+        *why = "negative size"; return false;
+    }
+    if (c->nbx < 0 || c->nby < 0) { *why = "negative bin count"; return false; }
+    if ((int64_t)(c->nbx + 1) * (c->nby + 1) > (int64_t)1 << 28) { *why = "too many cells"; return false; }
+    if (c->n_path_points >= ((int64_t)1 << 31)) { *why = "more than 2^31 path points"; return false; }
+    return true;
+}
+
+Layout make_layout(const tb2_config& c) {
+    const size_t N = (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
+    const size_t C = (size_t)(c.nbx + 1) * (size_t)(c.nby + 1), LC = (size_t)c.n_cell_lights;
+    const size_t R = sizeof(double);
+    Layout l{};
+    size_t b[B_COUNT];
+    b[B_POS0] = b[B_POS1] = N * 2 * R;
+    b[B_VEL] = N * 2 * R;
+    b[B_ROUTE_TIME] = N * R;
+    b[B_CURSOR] = b[B_PATH_END] = b[B_PATH_EFF_END] = N * 4;
+    b[B_PATH_XY] = P * 2 * R;
+    b[B_DEST_XY] = N * 2 * R;
+    b[B_D_NODE] = b[B_D_CAR] = b[B_D_LIGHT] = N * R;
+    b[B_CELL0] = b[B_CELL1] = N * 4;
+    b[B_LEADER] = N * 4;
+    b[B_TAB] = 3 * 2 * C * 4;
+    b[B_LIGHT_XY] = L * 2 * R;
+    b[B_SWITCH_TIME] = L * 8;
+    b[B_FACE_PTR] = (L + 1) * 4;
+    b[B_FACE_VEC] = F * 2 * R;
+    b[B_GO0] = b[B_GO1] = F;
+    b[B_CELL_LIGHT_PTR] = (C + 1) * 4;
+    b[B_CELL_LIGHT_IDX] = LC * 4;
+    b[B_T0] = b[B_T1] = 8;
+    size_t off = 0;
+    for (int i = 0; i < B_COUNT; ++i) {
+        l.off[i] = off;
+        l.bytes[i] = b[i];
+        off += align_up(b[i] ? b[i] : 1);
+    }
+    l.total = off;
+    return l;
+}
+
+}  // namespace
+
+struct tb2_sim {
+    tb2_config cfg;
+    Layout lay;
+    char* arena = nullptr;
+    bool owns_arena = false;
+    int n_cells = 0;
+    int cur_pos = 0, cur_cell = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
+    int last_cell_in = 0;  // cell buffer that held the bins of the last executed step's start positions
+    bool prepared = false;
+    int64_t launches = 0, steps = 0;
+    double log_free_over_stop = 0.0;
+
+    template <typename T>
+    T* buf(int b) const { return reinterpret_cast<T*>(arena + lay.off[b]); }
+};
+
+namespace {
+
+// map a public field to (internal buffer, element bytes, element count)
+int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) {
+    const tb2_config& c = s->cfg;
+    const size_t N = (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
+    const size_t R = sizeof(double);
+    switch (field) {
+        case TB2_POS: *b = s->cur_pos ? B_POS1 : B_POS0; *elem = R; *count = N * 2; return 0;
+        case TB2_VEL: *b = B_VEL; *elem = R; *count = N * 2; return 0;
+        case TB2_ROUTE_TIME: *b = B_ROUTE_TIME; *elem = R; *count = N; return 0;
+        case TB2_CURSOR: *b = B_CURSOR; *elem = 4; *count = N; return 0;
+        case TB2_PATH_END: *b = B_PATH_END; *elem = 4; *count = N; return 0;
+        case TB2_PATH_EFF_END: *b = B_PATH_EFF_END; *elem = 4; *count = N; return 0;
+        case TB2_PATH_XY: *b = B_PATH_XY; *elem = R; *count = P * 2; return 0;
+        case TB2_DEST_XY: *b = B_DEST_XY; *elem = R; *count = N * 2; return 0;
+        case TB2_D_NODE: *b = B_D_NODE; *elem = R; *count = N; return 0;
+        case TB2_D_CAR: *b = B_D_CAR; *elem = R; *count = N; return 0;
+        case TB2_D_LIGHT: *b = B_D_LIGHT; *elem = R; *count = N; return 0;
+        case TB2_CELL: *b = s->last_cell_in ? B_CELL1 : B_CELL0; *elem = 4; *count = N; return 0;
+        case TB2_LEADER: *b = B_LEADER; *elem = 4; *count = N; return 0;
+        case TB2_LIGHT_XY: *b = B_LIGHT_XY; *elem = R; *count = L * 2; return 0;
+        case TB2_SWITCH_TIME: *b = B_SWITCH_TIME; *elem = 8; *count = L; return 0;
+        case TB2_FACE_PTR: *b = B_FACE_PTR; *elem = 4; *count = L + 1; return 0;
+        case TB2_FACE_VEC: *b = B_FACE_VEC; *elem = R; *count = F * 2; return 0;
+        case TB2_FACE_GO: *b = s->cur_go ? B_GO1 : B_GO0; *elem = 1; *count = F; return 0;
+        case TB2_CELL_LIGHT_PTR: *b = B_CELL_LIGHT_PTR; *elem = 4; *count = (size_t)s->n_cells + 1; return 0;
+        case TB2_CELL_LIGHT_IDX: *b = B_CELL_LIGHT_IDX; *elem = 4; *count = (size_t)c.n_cell_lights; return 0;
+        case TB2_LIGHTS_TIME: *b = s->cur_t ? B_T1 : B_T0; *elem = 8; *count = 1; return 0;
+        default: return fail(TB2_ERR_INVALID, "unknown field id");
+    }
+}
+
+void fill_grid_args(const tb2_sim* s, StepArgs64* a) {
+    const tb2_config& c = s->cfg;
+    a->n_cars = c.n_cars; a->n_lights = c.n_lights; a->n_cells = s->n_cells;
+    a->car_blocks = (c.n_cars + 255) / 256;
+    a->nbx = c.nbx; a->nby = c.nby; a->ncx = c.nbx + 1; a->write_aux = c.write_aux;
+    a->ex0 = c.ex0; a->ex1 = c.ex1; a->exd = c.exd; a->ey0 = c.ey0; a->ey1 = c.ey1; a->eyd = c.eyd;
+    a->speed_limit = c.speed_limit; a->stop_distance = c.stop_distance; a->free_distance = c.free_distance;
+    a->default_acceleration = c.default_acceleration;
+    a->log_free_over_stop = s->log_free_over_stop;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb2_abi_version(void) { return TB2_ABI_VERSION; }
+const char* tb2_last_error(void) { return g_err.c_str(); }
+
+size_t tb2_arena_bytes(const tb2_config* cfg) {
+    std::string why;
+    if (!config_ok(cfg, &why)) { g_err = why; return 0; }
+    return make_layout(*cfg).total;
+}
+
+int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_sim** out) {
+    if (!out) return fail(TB2_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    std::string why;
+    if (!config_ok(cfg, &why)) return fail(TB2_ERR_INVALID, why);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(TB2_ERR_NO_DEVICE, "no CUDA device available - traffic_b200 has no CPU path");
+    }
+    tb2_sim* s = new (std::nothrow) tb2_sim();
+    if (!s) return fail(TB2_ERR_INVALID, "out of host memory");
+    s->cfg = *cfg;
+    s->lay = make_layout(*cfg);
+    s->n_cells = (cfg->nbx + 1) * (cfg->nby + 1);
+    s->log_free_over_stop = std::log(cfg->free_distance / cfg->stop_distance);  // host libm, simulation.py:180
+    if (arena_dev) {
+        if (arena_bytes < s->lay.total) { delete s; return fail(TB2_ERR_INVALID, "arena too small (see tb2_arena_bytes)"); }
+        if (reinterpret_cast<uintptr_t>(arena_dev) % kAlign) { delete s; return fail(TB2_ERR_INVALID, "arena must be 256-byte aligned"); }
+        s->arena = static_cast<char*>(arena_dev);
+    } else {
+        e = cudaMalloc(reinterpret_cast<void**>(&s->arena), s->lay.total);
+        if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(arena)"); }
+        s->owns_arena = true;
+    }
+    *out = s;
+    return TB2_OK;
+}
+
+int tb2_destroy(tb2_sim* s) {
+    if (!s) return TB2_OK;
+    if (s->owns_arena && s->arena) cudaFree(s->arena);
+    delete s;
+    return TB2_OK;
+}
+
+int tb2_field_info(const tb2_sim* s, int field, size_t* n_elems, size_t* elem_bytes) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    int b; size_t eb, cnt;
+    if (int rc = field_buf(s, field, &b, &eb, &cnt)) return rc;
+    if (n_elems) *n_elems = cnt;
+    if (elem_bytes) *elem_bytes = eb;
+    return TB2_OK;
+}
+
+void* tb2_field_ptr(const tb2_sim* s, int field) {
+    if (!s) return nullptr;
+    int b; size_t eb, cnt;
+    if (field_buf(s, field, &b, &eb, &cnt)) return nullptr;
+    return s->arena + s->lay.off[b];
+}
+
+int tb2_upload(tb2_sim* s, int field, const void* src, size_t bytes, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    int b; size_t eb, cnt;
+    if (int rc = field_buf(s, field, &b, &eb, &cnt)) return rc;
+    if (bytes != eb * cnt) {
+        char m[160];
+        snprintf(m, sizeof m, "tb2_upload(field %d): got %zu bytes, field holds %zu", field, bytes, eb * cnt);
+        return fail(TB2_ERR_INVALID, m);
+    }
+    if (bytes && !src) return fail(TB2_ERR_INVALID, "null source");
+    if (bytes) CU(cudaMemcpyAsync(s->arena + s->lay.off[b], src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    if (field == TB2_POS) s->prepared = false;
+    return TB2_OK;
+}
+
+int tb2_download(const tb2_sim* s, int field, void* dst, size_t bytes, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    int b; size_t eb, cnt;
+    if (int rc = field_buf(s, field, &b, &eb, &cnt)) return rc;
+    if (bytes != eb * cnt) {
+        char m[160];
+        snprintf(m, sizeof m, "tb2_download(field %d): got %zu bytes, field holds %zu", field, bytes, eb * cnt);
+        return fail(TB2_ERR_INVALID, m);
+    }
+    if (bytes && !dst) return fail(TB2_ERR_INVALID, "null destination");
+    if (bytes) CU(cudaMemcpyAsync(dst, s->arena + s->lay.off[b], bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return TB2_OK;
+}
+
+int tb2_prepare(tb2_sim* s, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    StepArgs64 g{};
+    fill_grid_args(s, &g);
+    launch_prepare_f64(s->cfg.n_cars, s->n_cells, s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0),
+                       s->buf<int32_t>(s->cur_cell ? B_CELL1 : B_CELL0), s->buf<int32_t>(B_TAB), s->cur_tab, g,
+                       (cudaStream_t)stream);
+    s->launches += s->cfg.n_cars > 0 ? 2 : 1;
+    s->last_cell_in = s->cur_cell;
+    CU(cudaGetLastError());
+    s->prepared = true;
+    return TB2_OK;
+}
+
+int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream_) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    if (n_steps < 0) return fail(TB2_ERR_INVALID, "negative n_steps");
+    if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
+    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (positions were uploaded since)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t C2 = (size_t)2 * s->n_cells;
+    StepArgs64 a{};
+    fill_grid_args(s, &a);
+    a.dt = dt;
+    a.vel = s->buf<double2>(B_VEL);
+    a.route_time = s->buf<double>(B_ROUTE_TIME);
+    a.cursor = s->buf<int32_t>(B_CURSOR);
+    a.path_end = s->buf<int32_t>(B_PATH_END);
+    a.path_eff_end = s->buf<int32_t>(B_PATH_EFF_END);
+    a.path_xy = s->buf<double2>(B_PATH_XY);
+    a.dest_xy = s->buf<double2>(B_DEST_XY);
+    a.d_node = s->buf<double>(B_D_NODE);
+    a.d_car = s->buf<double>(B_D_CAR);
+    a.d_light = s->buf<double>(B_D_LIGHT);
+    a.leader = s->buf<int32_t>(B_LEADER);
+    a.light_xy = s->buf<double2>(B_LIGHT_XY);
+    a.face_ptr = s->buf<int32_t>(B_FACE_PTR);
+    a.face_vec = s->buf<double2>(B_FACE_VEC);
+    a.cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
+    a.cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
+    a.switch_time = s->buf<double>(B_SWITCH_TIME);
+    for (int32_t k = 0; k < n_steps; ++k) {
+        if (order == TB2_ORDER_LIGHTS_CARS && k == 0) {
+            // L (C L) (C L) ... C : the first tick is its own launch, the rest ride in the step kernel
+            launch_lights_tick(s->cfg.n_lights, dt, a.switch_time, a.face_ptr, s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0),
+                               s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1), s->buf<double>(s->cur_t ? B_T1 : B_T0),
+                               s->buf<double>(s->cur_t ? B_T0 : B_T1), stream);
+            s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
+        }
+        a.tick = (order == TB2_ORDER_CARS_LIGHTS) ? 1 : (k < n_steps - 1 ? 1 : 0);
+        a.pos_in = s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0);
+        a.pos_out = s->buf<double2>(s->cur_pos ? B_POS0 : B_POS1);
+        a.cell_in = s->buf<int32_t>(s->cur_cell ? B_CELL1 : B_CELL0);
+        a.cell_out = s->buf<int32_t>(s->cur_cell ? B_CELL0 : B_CELL1);
+        int32_t* tab = s->buf<int32_t>(B_TAB);
+        a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
+        a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
+        a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
+        a.go_cur = s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0);
+        a.go_next = s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1);
+        a.t_cur = s->buf<double>(s->cur_t ? B_T1 : B_T0);
+        a.t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
+        launch_step_f64(a, stream);
+        s->launches++;
+        s->last_cell_in = s->cur_cell;
+        s->cur_pos ^= 1; s->cur_cell ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
+        if (a.tick) { s->cur_go ^= 1; s->cur_t ^= 1; }
+        s->steps++;
+    }
+    CU(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_step_host(tb2_sim* s, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
+                  void* frame_xy_out, uint8_t* face_go_out, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    const size_t F = (size_t)s->cfg.n_faces, N = (size_t)s->cfg.n_cars;
+    if (face_go_in) if (int rc = tb2_upload(s, TB2_FACE_GO, face_go_in, F, stream)) return rc;
+    if (int rc = tb2_step(s, dt, n_steps, order, stream)) return rc;
+    if (frame_xy_out) if (int rc = tb2_download(s, TB2_POS, frame_xy_out, N * 2 * sizeof(double), stream)) return rc;
+    if (face_go_out) if (int rc = tb2_download(s, TB2_FACE_GO, face_go_out, F, stream)) return rc;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return TB2_OK;
+}
+
+int64_t tb2_launch_count(const tb2_sim* s) { return s ? s->launches : 0; }
+int64_t tb2_step_count(const tb2_sim* s) { return s ? s->steps : 0; }
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Synthetic road worlds for the vehicle-update path (no network, no osmnx).
+
+The reference gets its map from OSMnx (``osm_request.py:5-67``): an object with ``.G`` (a networkx
+MultiDiGraph whose nodes carry projected ``x``/``y`` and whose edges carry ``length``), ``.axis``
+(xmin, xmax, ymin, ymax) and matplotlib ``.fig``/``.ax``.  ``SynthGraph`` is a duck-typed stand-in with the
+same attributes: a rotated, jittered grid at UTM-like coordinates.  The rotation keeps every
+edge off the coordinate axes (an axis-aligned edge has ``int(|dx|) == 0`` -> empty linspace -> the reference
+never detects anything on it, ``models.py:168`` / ``navigation.py:437``) and the jitter removes collinear
+path triples (``arccos(1 - ulp)`` razor edge).
+
+Everything here is host-side numpy; the arrays feed ``traffic_b200.state`` (the SoA packer).  networkx is only
+imported when ``.G`` is touched (the reference-facing facade and the golden-vector generator need it).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+
+BIN_SIZE = 200.0  # models.py:16
+
+
+class SynthGraph:
+    """Rotated + jittered ``nx_ x ny_`` grid, bidirectional edges, Euclidean ``length``.
+
+    Node ids are ``node_id_base + row * nx_ + col`` (row-major), so ``list(G.nodes())[:n]`` - which is what
+    ``navigation.find_nodes`` (``navigation.py:552-563``) hands to the reference initialiser - is the first n
+    nodes in that order.
+    """
+
+    def __init__(self, nx_: int, ny_: int, spacing: float = 100.0, x0: float = 566000.0, y0: float = 4186000.0,
+                 theta_deg: float = 29.0, jitter: float = 5.0, seed: int = 0, node_id_base: int = 1000):
+        self.nx, self.ny = int(nx_), int(ny_)
+        self.spacing = float(spacing)
+        self.node_id_base = int(node_id_base)
+        rng = np.random.default_rng(seed)
+        cols, rows = np.meshgrid(np.arange(self.nx, dtype=np.float64), np.arange(self.ny, dtype=np.float64))
+        gx = cols.ravel() * spacing
+        gy = rows.ravel() * spacing
+        th = math.radians(theta_deg)
+        # rotate about the grid centre so the bounding box stays roughly square
+        cx, cy = gx.mean(), gy.mean()
+        rx = (gx - cx) * math.cos(th) - (gy - cy) * math.sin(th)
+        ry = (gx - cx) * math.sin(th) + (gy - cy) * math.cos(th)
+        rx += rng.uniform(-jitter, jitter, rx.shape)
+        ry += rng.uniform(-jitter, jitter, ry.shape)
+        rx -= rx.min()
+        ry -= ry.min()
+        self.node_xy = np.stack([x0 + rx, y0 + ry], axis=1)  # (n, 2) float64
+        n = self.nx * self.ny
+        self.node_ids = self.node_id_base + np.arange(n, dtype=np.int64)
+        idx = np.arange(n).reshape(self.ny, self.nx)
+        right = np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1)
+        up = np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()], 1)
+        und = np.concatenate([right, up], 0)
+        # directed both ways; order: for each undirected edge (u, v) then (v, u)
+        self.edge_u = np.concatenate([und[:, 0], und[:, 1]])
+        self.edge_v = np.concatenate([und[:, 1], und[:, 0]])
+        d = self.node_xy[self.edge_v] - self.node_xy[self.edge_u]
+        self.edge_len = np.hypot(d[:, 0], d[:, 1])
+        xmin, ymin = self.node_xy.min(0)
+        xmax, ymax = self.node_xy.max(0)
+        w, h = xmax - xmin, ymax - ymin
+        self.axis = (xmin - 0.02 * w, xmax + 0.02 * w, ymin - 0.02 * h, ymax + 0.02 * h)
+        self.fig = None
+        self.ax = SimpleNamespace(axis=lambda: self.axis)  # environment.py:24,29 reads graph.ax.axis()
+        self._G = None
+
+    @property
+    def n_nodes(self) -> int:
+        return self.nx * self.ny
+
+    @property
+    def G(self):
+        """networkx MultiDiGraph view (built lazily; nodes inserted in row-major order)."""
+        if self._G is None:
+            import networkx as nx
+
+            G = nx.MultiDiGraph()
+            for i, nid in enumerate(self.node_ids):
+                G.add_node(int(nid), x=float(self.node_xy[i, 0]), y=float(self.node_xy[i, 1]))
+            for u, v, ln in zip(self.edge_u, self.edge_v, self.edge_len):
+                G.add_edge(int(self.node_ids[u]), int(self.node_ids[v]), length=float(ln))
+            self._G = G
+        return self._G
+
+    def csr(self):
+        """(indptr, indices, weights) of the directed graph, node *indices* (not ids)."""
+        import scipy.sparse as sp
+
+        n = self.n_nodes
+        m = sp.csr_matrix((self.edge_len, (self.edge_u, self.edge_v)), shape=(n, n))
+        return m
+
+
+def grid_dims(axis, bin_size: float = BIN_SIZE):
+    """Number of bin edges per axis, exactly as ``np.arange(axis[0], axis[1], 200)`` (``models.py:16``)."""
+    nbx = len(np.arange(axis[0], axis[1], bin_size))
+    nby = len(np.arange(axis[2], axis[3], bin_size))
+    return nbx, nby
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Large-world generators (configs c3/c4/c5 of SURVEY.md §8(d)): same schema as the reference initialisers
+# (``simulation.py:189-256, 329-381``) but vectorised - the reference's one-car-per-node, two-networkx-Dijkstras-
+# per-car initialiser cannot make 50k cars on 10k nodes.
+# ----------------------------------------------------------------------------------------------------------------
+
+def make_routes(graph: SynthGraph, n_cars: int, max_hops: int = 40, n_sources: int = 512, seed: int = 0,
+                max_points: int = 64):
+    """True shortest paths (by ``length``) for ``n_cars`` cars from a bounded set of source nodes.
+
+    Returns ``(path_ptr[int64 N+1], path_xy[float64 P,2], origin_idx, dest_idx)``.  The path of a car is the
+    polyline of node positions origin..destination - what ``navigation.shortest_path_lines_nx`` +
+    ``models.path_decompiler`` (``navigation.py:801-841``, ``models.py:116-137``) produce on a graph without
+    edge ``geometry``: per edge the two endpoints, consecutive duplicates dropped.
+    """
+    from scipy.sparse.csgraph import dijkstra
+
+    rng = np.random.default_rng(seed)
+    n = graph.n_nodes
+    m = graph.csr()
+    n_sources = int(min(n_sources, n))
+    sources = rng.choice(n, size=n_sources, replace=False)
+    limit = (max_hops + 2) * graph.spacing * 1.2
+    dist, pred = dijkstra(m, directed=True, indices=sources, return_predecessors=True, limit=limit)
+    # hop distance on the grid bounds the polyline length
+    src_of_car = rng.integers(0, n_sources, size=n_cars)
+    origin = sources[src_of_car]
+    orow, ocol = origin // graph.nx, origin % graph.nx
+    hops_total = rng.integers(2, max(3, min(max_hops, max_points - 1)) + 1, size=n_cars)
+    frac = rng.random(n_cars)
+    dr = np.rint(hops_total * frac).astype(np.int64) * rng.choice([-1, 1], n_cars)
+    dc = (hops_total - np.abs(dr)) * rng.choice([-1, 1], n_cars)
+    drow = np.clip(orow + dr, 0, graph.ny - 1)
+    dcol = np.clip(ocol + dc, 0, graph.nx - 1)
+    dest = drow * graph.nx + dcol
+    same = dest == origin
+    # nudge degenerate destinations one node away (an empty route parks the car from t=0, Appendix B-15;
+    # we keep a few of those on purpose in the small configs but not here)
+    dest[same] = np.where(ocol[same] + 1 < graph.nx, origin[same] + 1, origin[same] - 1)
+    # walk predecessors dest -> origin (vectorised over cars)
+    cur = dest.copy()
+    rev = [cur.copy()]
+    alive = cur != origin
+    for _ in range(max_points + 8):
+        if not alive.any():
+            break
+        nxt = pred[src_of_car, cur]
+        nxt = np.where(alive, nxt, cur)
+        unreachable = nxt < 0
+        if unreachable.any():
+            raise RuntimeError("destination outside the Dijkstra limit; raise `limit`")
+        cur = nxt
+        rev.append(np.where(alive, cur, -1))
+        alive = cur != origin
+    rev = np.stack(rev, 1)  # (N, Lmax) dest .. origin then -1 padding
+    length = (rev >= 0).sum(1)
+    # reverse each row into origin .. dest order
+    Lmax = rev.shape[1]
+    ar = np.arange(Lmax)[None, :]
+    gather = length[:, None] - 1 - ar
+    valid = gather >= 0
+    fwd = np.take_along_axis(rev, np.where(valid, gather, 0), 1)
+    # cap at max_points
+    length = np.minimum(length, max_points)
+    valid &= ar < length[:, None]
+    path_ptr = np.zeros(n_cars + 1, np.int64)
+    np.cumsum(length, out=path_ptr[1:])
+    nodes_flat = fwd[valid]
+    path_xy = graph.node_xy[nodes_flat]
+    dest_eff = fwd[np.arange(n_cars), length - 1]
+    return path_ptr, path_xy, origin, dest_eff
+
+
+def make_lights(graph: SynthGraph, prescale: int = 10, seed: int = 0):
+    """Vectorised restatement of ``simulation.init_traffic_lights`` (``simulation.py:329-381``) on a grid graph.
+
+    Lights sit on every ``prescale``-th node in node order (every grid node has MultiDiGraph degree > 3,
+    ``navigation.py:545-547``); a light's faces are the vectors to its out-neighbours in adjacency insertion order
+    (``navigation.determine_pedigree``, ``navigation.py:501-521`` - on a jittered grid the shortest path to an
+    out-neighbour is the direct edge), ``switch-time = round(U(0,1) * degree, 2)`` (``models.py:31-38``) and the
+    initial ``go`` pattern is ``[False, True, False, ...]`` (``simulation.py:355-356``).
+    """
+    rng = np.random.default_rng(seed)
+    n = graph.n_nodes
+    light_nodes = np.arange(0, n, prescale)
+    # adjacency insertion order of SynthGraph.G: edges are added (right u->v) for all, (up u->v) for all,
+    # then the reverses; out-neighbour order per node = right, up, left, down (those that exist)
+    r, c = light_nodes // graph.nx, light_nodes % graph.nx
+    cand = np.stack([np.where(c + 1 < graph.nx, light_nodes + 1, -1),
+                     np.where(r + 1 < graph.ny, light_nodes + graph.nx, -1),
+                     np.where(c - 1 >= 0, light_nodes - 1, -1),
+                     np.where(r - 1 >= 0, light_nodes - graph.nx, -1)], 1)
+    has = cand >= 0
+    degree = has.sum(1)
+    face_ptr = np.zeros(len(light_nodes) + 1, np.int32)
+    np.cumsum(degree, out=face_ptr[1:])
+    owner = np.repeat(np.arange(len(light_nodes)), 4).reshape(-1, 4)[has]
+    nb = cand[has]
+    face_vec = graph.node_xy[nb] - graph.node_xy[light_nodes[owner]]
+    k_in_light = np.arange(len(nb)) - face_ptr[owner]
+    face_go = (k_in_light % 2 == 1)
+    switch_time = np.round(rng.random(len(light_nodes)) * degree, 2)
+    return dict(node=graph.node_ids[light_nodes], xy=graph.node_xy[light_nodes].copy(), degree=degree.astype(np.int32),
+                switch_time=switch_time, face_ptr=face_ptr, face_vec=face_vec, face_go=face_go)
