@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the per-timestep vehicle update (the loop of test/profile_cars_update.py:28-34) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4_city_1m] [--impl reference]
+
+One "step" = one simulation timestep over every car of the workload (Cars.update + TrafficLights.update, in the
+profile script's order).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions:
+  value     vehicle-updates/s with the state resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       the same metric through the host-buffer C-ABI call tb2_step_host: per frame interval, H2D of the light-face
+            states from pinned memory, k steps, D2H of the position frame + face states (north_star: frames every k steps)
+  roofline  algorithmic bytes per car-step x cars / mean step-kernel duration vs the measured HBM peak
+  cpu_baseline  the C oracle port of the reference, one thread, on a bounded sample of the same workload
+With --gpus N (torchrun, one rank per GPU) every rank advances an independent replica of the workload (the path
+shards only by replica); a small NCCL all_gather collects per-replica trip statistics.
+--impl reference times the reference's CPU algorithm (the oracle port, all host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+# algorithmic bytes per car-step of the fused fp64 step kernel (DESIGN.md §Kernels, table "step_f64"):
+#   reads : pos 16, route_time 8, cursor 4, path_end 4, path_eff_end 4, cell 4, view (3 polyline points) 48,
+#           cell-table entry 8, candidate position 16                                   = 112
+#   writes: pos 16, vel 16, route_time 8, d_node/d_car/d_light 24, leader 4, next cell 4,
+#           two 4-byte atomics into the next cell table 8                               = 80
+ALGO_BYTES = {"f64": 192.0}
+L2_BYTES = 126e6
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[1])); power.append(float(f[3]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample we have
+            for ts, ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w": float(np.median(power)) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(name, seed):
+    from traffic_b200 import synth
+    cfg = dict(synth.CITY_CONFIGS[name])
+    cfg["seed"] = seed
+    w, _ = synth.make_city(**cfg)
+    return w
+
+
+def cpu_port_updates_per_s(w, dt, order, budget_s, threads):
+    """Time the C oracle (the CPU port of the reference algorithm) on a bounded sample of the workload."""
+    from oracle import oracle
+    wc = w.copy()
+    oracle.run(wc, dt, 1, order, threads=threads)  # warm caches / page in
+    steps, t_used = 0, 0.0
+    chunk = 2
+    while t_used < budget_s and steps < 4000:
+        t0 = time.perf_counter()
+        oracle.run(wc, dt, chunk, order, threads=threads)
+        t_used += time.perf_counter() - t0
+        steps += chunk
+        chunk = min(chunk * 2, 256)
+    return w.n_cars * steps / t_used, steps, t_used
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to the
+    GPU box) with every host thread, same workload / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    w = make_workload(args.workload, args.seed)
+    dt, order = args.dt, 0
+    for _ in range(args.warmup):
+        oracle.run(w, dt, 1, order, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.run(w, dt, 1, order, threads=cores)
+    el = time.perf_counter() - t0
+    val = w.n_cars * args.steps / el
+    line = {"impl": "reference", "metric": "vehicle-updates/sec", "value": val, "unit": "vehicle-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "cars": w.n_cars, "lights": w.n_lights, "dt": dt,
+                       "order": "cars_then_lights"},
+            "cpu_baseline": {"value": val, "unit": "vehicle-updates/s", "cores": cores, "kind": "port",
+                             "sample": "the full workload, %d timed steps, pthread fan-out over cars" % args.steps},
+            "e2e": {"value": val, "unit": "vehicle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "C port of the reference algorithm (oracle/traffic_oracle.c, pinned bit-exact to the reference's "
+                    "golden vectors); the unmodified Python reference measured 300-450 vehicle-updates/s on one core "
+                    "(tests/golden/*.npz ref_updates_per_s)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--workload", default="c4_city_1m")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dt", type=float, default=1e-3)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--frame-every", type=int, default=100, help="k: steps between position frames in the e2e leg")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the secondary 2k-car measurement")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from traffic_b200 import native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dt, order = args.dt, native.ORDER_CARS_LIGHTS  # the profile script's order
+    w = make_workload(args.workload, args.seed + rank)  # every rank: an independent replica (different seed)
+    sim = native.DeviceSim(w, write_aux=True)
+    N = w.n_cars
+
+    # ---- device-resident throughput ----
+    sim.step(dt, args.warmup, order)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = sim.launch_count
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    sim.step(dt, args.steps, order)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = sim.launch_count - l0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    cars_total = torch.tensor([float(N)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cars_total, op=dist.ReduceOp.SUM)
+    ms_max = float(tmax.item())
+    value = float(cars_total.item()) * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    k = max(1, min(args.frame_every, args.steps))
+    frames = max(1, args.steps // k)
+    frame = torch.empty((N, 2), dtype=torch.float64).pin_memory()
+    go_in = torch.from_numpy(sim.download(native.FACE_GO).copy()).pin_memory()
+    go_out = torch.empty_like(go_in).pin_memory()
+    sim.step_host(dt, k, order, go_in, frame, go_out)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        go_in.copy_(go_out)
+        sim.step_host(dt, k, order, go_in, frame, go_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = float(cars_total.item()) * frames * k / float(te.item())
+    h2d = go_in.numel() / k
+    d2h = (frame.numel() * 8 + go_out.numel()) / k
+
+    # ---- replica statistics gathered over NCCL (the only collective on this path) ----
+    rt = sim.tensor(native.ROUTE_TIME)
+    cur = sim.tensor(native.CURSOR)
+    end = sim.tensor(native.PATH_END)
+    stats = torch.stack([rt.mean(), (cur >= end).double().mean()]).to(torch.float32)
+    if world > 1:
+        allstats = torch.empty(world * 2, device="cuda", dtype=torch.float32)
+        dist.all_gather_into_tensor(allstats, stats)
+    else:
+        allstats = stats
+    allstats = allstats.cpu().numpy().reshape(-1, 2)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kernel_us = ms / launches * 1e3 if launches else float("nan")
+        algo = ALGO_BYTES["f64"] * N
+        achieved = algo / (kernel_us * 1e-6) / 1e9
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "traffic_bytes.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload + ":f64")
+            except Exception:
+                traffic = None
+        ws = N * 136 + min(len(w.path_xy) * 16, N * 64)
+        line = {
+            "metric": "vehicle-updates/sec", "value": value, "unit": "vehicle-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "cars_per_gpu": N, "lights": w.n_lights, "faces": w.n_faces,
+                       "path_points": int(len(w.path_xy)), "cells": w.grid.n_cells, "dt": dt,
+                       "order": "cars_then_lights", "replicas": world, "parallelism": "replica-per-gpu",
+                       "l2": "working set %.0f MB per step > %.0f MB L2, no explicit flush" % (ws / 1e6, L2_BYTES / 1e6),
+                       "frame_every_k_steps": k},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "step_f64_kernel", "kernel_us": kernel_us,
+                         "algorithmic_bytes_per_car_step": ALGO_BYTES["f64"], "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": "vehicle-updates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "frames": frames, "steps_per_frame": k},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "replica_stats": {"mean_route_time": [float(x) for x in allstats[:, 0]],
+                              "parked_fraction": [float(x) for x in allstats[:, 1]]},
+        }
+        if not args.no_cpu_baseline:
+            v, s_, t_ = cpu_port_updates_per_s(w, dt, order, args.cpu_budget, threads=1)
+            line["cpu_baseline"] = {"value": v, "unit": "vehicle-updates/s", "cores": 1, "kind": "port",
+                                    "sample": "%d steps of the same %d-car workload (%.1f s), C oracle port, 1 thread; "
+                                              "the unmodified Python reference runs 300-450 updates/s on one core"
+                                              % (s_, N, t_)}
+        if not args.no_small and args.workload != "c2_manhattan_2k":
+            w2 = make_workload("c2_manhattan_2k", args.seed)
+            s2 = native.DeviceSim(w2)
+            s2.step(dt, 200, order)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            s2.step(dt, 2000, order)
+            a1.record()
+            torch.cuda.synchronize()
+            ms2 = a0.elapsed_time(a1)
+            line["also"] = {"workload": "c2_manhattan_2k", "cars": w2.n_cars, "steps": 2000,
+                            "value": w2.n_cars * 2000 / (ms2 * 1e-3), "unit": "vehicle-updates/s",
+                            "us_per_step": ms2 / 2000 * 1e3}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

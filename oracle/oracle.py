@@ -56,8 +56,7 @@ def params_of(w) -> ToParams:
 def run(w, dt: float, n_steps: int, order: int = ORDER_CARS_LIGHTS, threads: int | None = None) -> None:
     """Advance ``w`` in place by ``n_steps`` steps."""
     L = lib()
-    if threads is not None:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+    L.to_set_threads(C.c_int(1 if threads is None else int(threads)))
     P = params_of(w)
     t = C.c_double(w.lights_time)
     L.to_run(C.byref(P), C.c_double(dt), C.c_int(n_steps), C.c_int(order), C.byref(t),

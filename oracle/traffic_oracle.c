@@ -15,9 +15,16 @@
  * reach for 2-vectors) evaluates x0*y0 then fma(x1, y1, .) - measured on the fixture machine, 200000/200000.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* number of worker threads for the per-car loops (cars are independent within a step: every read of another car
+ * uses start-of-step values).  1 = the reference's own single-threaded execution. */
+static int g_threads = 1;
+void to_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+int to_get_threads(void) { return g_threads; }
 
 typedef struct {
     int32_t n_cars, n_lights, n_faces;
@@ -141,28 +148,38 @@ static void build_cell_min2(int n, const int32_t* cell, int n_cells, int32_t* mi
 
 /* One Cars.update(dt, lights)   cars.py:61-95 (+ find_obstacles 98-106, simulation.update_cars 20-80).
  * pos_new is scratch (N,2); min12 is scratch (2*n_cells). */
-void to_cars_update(const to_params* P, double dt,
-                    double* pos, double* vel, double* route_time, int32_t* cursor,
-                    const int32_t* path_end, const int32_t* path_eff_end,
-                    const double* path_xy, const double* dest_xy,
-                    double* d_node_o, double* d_car_o, double* d_light_o, int32_t* cell, int32_t* leader,
-                    const double* light_xy, const int32_t* face_ptr, const double* face_vec, const uint8_t* face_go,
-                    const int32_t* cell_light_ptr, const int32_t* cell_light_idx,
-                    double* pos_new, int32_t* min12)
-{
-    const int n = P->n_cars;
-    const int ncx = P->nbx + 1, ncy = P->nby + 1;
-    /* models.determine_bins   models.py:7-19, cars.py:78 */
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; ++i) {
-        int xb = digitize_(pos[2 * i], P->nbx, P->ex0, P->ex1, P->exd);
-        int yb = digitize_(pos[2 * i + 1], P->nby, P->ey0, P->ey1, P->eyd);
-        cell[i] = yb * ncx + xb;
-    }
-    build_cell_min2(n, cell, ncx * ncy, min12);
+typedef struct {
+    const to_params* P; double dt;
+    double* pos; double* vel; double* route_time; int32_t* cursor;
+    const int32_t* path_end; const int32_t* path_eff_end; const double* path_xy; const double* dest_xy;
+    double* d_node_o; double* d_car_o; double* d_light_o; int32_t* cell; int32_t* leader;
+    const double* light_xy; const int32_t* face_ptr; const double* face_vec; const uint8_t* face_go;
+    const int32_t* cell_light_ptr; const int32_t* cell_light_idx; double* pos_new; int32_t* min12;
+    int phase, lo, hi;
+} car_job;
 
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; ++i) {
+static void cars_range(const car_job* J)
+{
+    const to_params* P = J->P; const double dt = J->dt;
+    double* pos = J->pos; double* vel = J->vel; double* route_time = J->route_time; int32_t* cursor = J->cursor;
+    const int32_t* path_end = J->path_end; const int32_t* path_eff_end = J->path_eff_end;
+    const double* path_xy = J->path_xy; const double* dest_xy = J->dest_xy;
+    double* d_node_o = J->d_node_o; double* d_car_o = J->d_car_o; double* d_light_o = J->d_light_o;
+    int32_t* cell = J->cell; int32_t* leader = J->leader;
+    const double* light_xy = J->light_xy; const int32_t* face_ptr = J->face_ptr; const double* face_vec = J->face_vec;
+    const uint8_t* face_go = J->face_go; const int32_t* cell_light_ptr = J->cell_light_ptr;
+    const int32_t* cell_light_idx = J->cell_light_idx; double* pos_new = J->pos_new; const int32_t* min12 = J->min12;
+    const int ncx = P->nbx + 1;
+    if (J->phase == 0) {
+        /* models.determine_bins   models.py:7-19, cars.py:78 */
+        for (int i = J->lo; i < J->hi; ++i) {
+            int xb = digitize_(pos[2 * i], P->nbx, P->ex0, P->ex1, P->exd);
+            int yb = digitize_(pos[2 * i + 1], P->nby, P->ey0, P->ey1, P->eyd);
+            cell[i] = yb * ncx + xb;
+        }
+        return;
+    }
+    for (int i = J->lo; i < J->hi; ++i) {
         const double x = pos[2 * i], y = pos[2 * i + 1];
         const int cur = cursor[i], end = path_end[i];
         const int has_path = cur < path_eff_end[i];        /* navigation.py:37-39 */
@@ -260,6 +277,41 @@ void to_cars_update(const to_params* P, double dt,
         /* Euler   cars.py:89-90 */
         pos_new[2 * i] = x + vx * dt; pos_new[2 * i + 1] = y + vy * dt;
     }
+}
+
+static void* cars_thread(void* arg) { cars_range((const car_job*)arg); return NULL; }
+
+static void fan_out(car_job* proto, int phase, int n)
+{
+    int T = g_threads;
+    if (T > n / 256 + 1) T = n / 256 + 1;
+    car_job jobs[256]; pthread_t th[256];
+    for (int t = 0; t < T; ++t) {
+        jobs[t] = *proto; jobs[t].phase = phase;
+        jobs[t].lo = (int)((int64_t)n * t / T); jobs[t].hi = (int)((int64_t)n * (t + 1) / T);
+    }
+    for (int t = 1; t < T; ++t) pthread_create(&th[t], NULL, cars_thread, &jobs[t]);
+    cars_range(&jobs[0]);
+    for (int t = 1; t < T; ++t) pthread_join(th[t], NULL);
+}
+
+void to_cars_update(const to_params* P, double dt,
+                    double* pos, double* vel, double* route_time, int32_t* cursor,
+                    const int32_t* path_end, const int32_t* path_eff_end,
+                    const double* path_xy, const double* dest_xy,
+                    double* d_node_o, double* d_car_o, double* d_light_o, int32_t* cell, int32_t* leader,
+                    const double* light_xy, const int32_t* face_ptr, const double* face_vec, const uint8_t* face_go,
+                    const int32_t* cell_light_ptr, const int32_t* cell_light_idx,
+                    double* pos_new, int32_t* min12)
+{
+    const int n = P->n_cars;
+    const int ncx = P->nbx + 1, ncy = P->nby + 1;
+    car_job J = { P, dt, pos, vel, route_time, cursor, path_end, path_eff_end, path_xy, dest_xy, d_node_o, d_car_o,
+                  d_light_o, cell, leader, light_xy, face_ptr, face_vec, face_go, cell_light_ptr, cell_light_idx,
+                  pos_new, min12, 0, 0, 0 };
+    fan_out(&J, 0, n);
+    build_cell_min2(n, cell, ncx * ncy, min12);
+    fan_out(&J, 1, n);
     memcpy(pos, pos_new, sizeof(double) * 2 * (size_t)n);
 }
 

@@ -1,0 +1,195 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (libtraffic_b200.so via
+traffic_b200.native), against (1) golden vectors recorded from the unmodified reference and (2) the C oracle on
+seeded synthetic worlds, plus size-independent properties at the 1M-car bench size.
+
+Bar: every discrete output - route cursor, bin/cell, leader index, light-face state, truthiness/None-ness of the
+obstacle distances - bit-exact at every step; floats within FLOAT_RTOL (relative to max(|ref|, 1)); the north_star
+tolerance is 1e-5 over 1,000 steps, the fp64 path is held to 1e-9."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_RTOL = 1e-9
+
+
+def _native():
+    from traffic_b200 import native
+    return native
+
+
+@pytest.mark.parametrize("name", util.golden_names())
+def test_cuda_matches_reference_golden(name):
+    native = _native()
+    g = util.load_golden(name)
+    w = util.world_from_golden(g)
+    start = w.path_start.copy()
+    sim = native.DeviceSim(w)
+    dt, T, order = float(g["dt"]), int(g["steps"]), util.order_code(g)
+    report, worst = [], 0.0
+    for t in range(T):
+        sim.step(dt, 1, order)
+        sim.download_world(w)
+        ok, m = util.compare_step(util.snapshot(w, start), g, t, w.grid.ncx, FLOAT_RTOL, report)
+        worst = max(worst, m)
+        if not ok:
+            break
+    assert not report, "\n".join(report[:10])
+    print("%s: %d steps bit-exact discrete, worst float rel err %.2e" % (name, T, worst))
+
+
+@pytest.mark.parametrize("name", util.golden_names()[:3])
+def test_cuda_multistep_launch_equals_single_steps(name):
+    """tb2_step(n_steps=k) must equal k calls of n_steps=1 (the lights tick rides in the step kernel)."""
+    native = _native()
+    g = util.load_golden(name)
+    order = util.order_code(g)
+    dt = float(g["dt"])
+    T = min(int(g["steps"]), 200)
+    w1 = util.world_from_golden(g)
+    start = w1.path_start.copy()
+    sim = native.DeviceSim(w1)
+    sim.step(dt, T, order)
+    sim.download_world(w1)
+    report = []
+    ok, worst = util.compare_step(util.snapshot(w1, start), g, T - 1, w1.grid.ncx, FLOAT_RTOL, report)
+    assert ok, "\n".join(report)
+
+
+def _compare_worlds(a, b, rtol, what):
+    for f in ("cursor", "cell", "leader", "face_go"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), "%s: %s differs at %s" % (
+            what, f, np.flatnonzero(getattr(a, f) != getattr(b, f))[:8])
+    assert np.array_equal(a.d_car != 0, b.d_car != 0), what + ": d_car truthiness"
+    assert np.array_equal(util.light_code(a.d_light), util.light_code(b.d_light)), what + ": d_light code"
+    worst = 0.0
+    for f in ("pos", "vel", "route_time", "d_node", "d_car", "d_light"):
+        x, y = getattr(a, f), getattr(b, f)
+        err = np.abs(x - y) / np.maximum(np.abs(y), 1.0)
+        err[np.isnan(x) & np.isnan(y)] = 0
+        m = float(np.nan_to_num(err, nan=np.inf).max()) if err.size else 0.0
+        worst = max(worst, m)
+        assert m <= rtol, "%s: %s rel err %.3e" % (what, f, m)
+    return worst
+
+
+@pytest.mark.parametrize("cfg,steps,chunk,order", [
+    (dict(nx_=40, ny_=40, n_cars=20000, prescale=3, seed=11), 300, 25, 1),
+    (dict(nx_=64, ny_=64, n_cars=2000, prescale=10, seed=12, x0=583000.0, y0=4507000.0), 1000, 100, 0),
+    (dict(nx_=100, ny_=100, n_cars=50000, prescale=10, seed=13), 200, 50, 1),
+])
+def test_cuda_matches_oracle_synthetic(cfg, steps, chunk, order):
+    """Same seeded world through the CUDA path and the C oracle, compared every `chunk` steps."""
+    native = _native()
+    from oracle import oracle
+    from traffic_b200 import synth
+
+    w_gpu, _ = synth.make_city(**cfg)
+    w_cpu = w_gpu.copy()
+    sim = native.DeviceSim(w_gpu)
+    dt = 1e-3
+    worst = 0.0
+    for s in range(0, steps, chunk):
+        sim.step(dt, chunk, order)
+        oracle.run(w_cpu, dt, chunk, order)
+        sim.download_world(w_gpu)
+        worst = max(worst, _compare_worlds(w_gpu, w_cpu, FLOAT_RTOL, "step %d" % (s + chunk)))
+    assert (w_cpu.leader >= 0).sum() > 0 and (w_cpu.d_light != 0).sum() > 0, "test world exercises no obstacles"
+    print("synthetic %s: %d steps, worst float rel err %.2e" % (cfg, steps, worst))
+
+
+def test_edge_cases_empty_and_parked():
+    """No cars / no lights / cars with empty routes (parked from t=0, Appendix B-15) / single-point routes."""
+    native = _native()
+    from oracle import oracle
+    from traffic_b200.state import make_world
+
+    axis = (566000.0, 567000.0, 4186000.0, 4187000.0)
+    # empty world
+    w = make_world(axis, np.zeros((0, 2)), np.zeros(1, np.int64), np.zeros((0, 2)), np.zeros((0, 2)))
+    sim = native.DeviceSim(w)
+    sim.step(0.1, 3, 0)
+    sim.download_world(w)
+    assert abs(w.lights_time - 0.30000000000000004) < 1e-15 and sim.step_count == 3
+    # ragged: route lengths 0, 1, 2, 5; two cars sharing a cell and a segment
+    pos = np.array([[566100.0, 4186100.0], [566150.0, 4186130.0], [566160.0, 4186140.0], [566500.0, 4186500.0]])
+    paths = [np.zeros((0, 2)), np.array([[566190.0, 4186170.0]]), np.array([[566250.0, 4186230.0], [566300.0, 4186400.0]]),
+             np.array([[566520.0, 4186530.0], [566600.0, 4186640.0], [566700.0, 4186650.0], [566800.0, 4186800.0], [566900.0, 4186820.0]])]
+    ptr = np.concatenate([[0], np.cumsum([len(p) for p in paths])])
+    dest = np.array([[566100.0, 4186100.0], [566190.0, 4186170.0], [566300.0, 4186400.0], [566900.0, 4186820.0]])
+    w_gpu = make_world(axis, pos, ptr, np.concatenate(paths), dest)
+    w_cpu = w_gpu.copy()
+    sim = native.DeviceSim(w_gpu)
+    for s in range(40):
+        sim.step(1e-3, 5, 1)
+        oracle.run(w_cpu, 1e-3, 5, 1)
+        sim.download_world(w_gpu)
+        _compare_worlds(w_gpu, w_cpu, FLOAT_RTOL, "ragged step %d" % (5 * s + 5))
+    assert w_cpu.cursor[0] == w_cpu.path_end[0] and (w_cpu.vel[0] == 0).all()
+
+
+def test_error_paths():
+    native = _native()
+    from traffic_b200.state import make_world
+    axis = (0.0, 1000.0, 0.0, 1000.0)
+    w = make_world(axis, np.array([[10.0, 10.0]]), np.array([0, 1]), np.array([[50.0, 60.0]]), np.array([[50.0, 60.0]]))
+    sim = native.DeviceSim(w)
+    with pytest.raises(native.NativeError):
+        sim.upload(native.POS, np.zeros(7))           # wrong size
+    sim.upload(native.POS, np.array([[20.0, 20.0]]))
+    with pytest.raises(native.NativeError):
+        sim.step(0.1, 1, 0)                           # positions changed, no prepare
+    with pytest.raises(native.NativeError):
+        native._check(sim.L.tb2_step(sim.h, 0.1, 1, 7, None), "tb2_step")  # bad order
+
+
+def test_properties_at_bench_size():
+    """1M-car city (BASELINE configs[3]): determinism, cursor monotonicity, route-time bookkeeping, leader validity,
+    light-table consistency - checks that do not need the CPU oracle at this size - plus a 20-step oracle cross-check."""
+    native = _native()
+    from oracle import oracle
+    from traffic_b200 import synth
+
+    w0, _ = synth.make_city(**synth.CITY_CONFIGS["c4_city_1m"])
+    dt, steps = 1e-3, 200
+    runs = []
+    for rep in range(2):
+        w = w0.copy()
+        sim = native.DeviceSim(w)
+        sim.step(dt, steps, 1)
+        sim.download_world(w)
+        runs.append(w)
+        del sim
+    a, b = runs
+    for f in ("pos", "vel", "route_time", "cursor", "d_node", "d_car", "d_light", "cell", "leader", "face_go"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), "non-deterministic field " + f
+    assert (a.cursor >= w0.cursor).all() and (a.cursor <= a.path_end).all()
+    moving = a.cursor < a.path_eff_end
+    assert np.allclose(a.route_time[moving], steps * dt, rtol=0, atol=1e-12)
+    lead = a.leader
+    has = lead >= 0
+    assert has.sum() > 1000
+    assert (lead[has] != np.flatnonzero(has)).all()
+    assert np.array_equal(a.cell[lead[has]], a.cell[has]), "leader not in my cell"
+    # leader is the smallest other index in the cell
+    order_ = np.lexsort((np.arange(len(a.cell)), a.cell))
+    first = np.full(a.grid.n_cells, -1, np.int64)
+    second = np.full(a.grid.n_cells, -1, np.int64)
+    sc = a.cell[order_]
+    head = np.r_[True, sc[1:] != sc[:-1]]
+    first[sc[head]] = order_[head]
+    sec = np.r_[False, head[:-1]] & ~head
+    second[sc[sec]] = order_[sec]
+    idx = np.flatnonzero(has)
+    want = np.where(first[a.cell[idx]] != idx, first[a.cell[idx]], second[a.cell[idx]])
+    assert np.array_equal(lead[idx], want)
+    # 20-step oracle cross-check from the same start
+    w_cpu = w0.copy()
+    w_gpu = w0.copy()
+    sim = native.DeviceSim(w_gpu)
+    sim.step(dt, 20, 1)
+    oracle.run(w_cpu, dt, 20, 1)
+    sim.download_world(w_gpu)
+    _compare_worlds(w_gpu, w_cpu, FLOAT_RTOL, "1M cars, 20 steps")

@@ -107,14 +107,18 @@ def grid_dims(axis, bin_size: float = BIN_SIZE):
 # per-car initialiser cannot make 50k cars on 10k nodes.
 # ----------------------------------------------------------------------------------------------------------------
 
-def make_routes(graph: SynthGraph, n_cars: int, max_hops: int = 40, n_sources: int = 512, seed: int = 0,
-                max_points: int = 64):
-    """True shortest paths (by ``length``) for ``n_cars`` cars from a bounded set of source nodes.
+def make_routes(graph: SynthGraph, n_cars: int, max_hops: int = 40, n_sources: int = 256, seed: int = 0,
+                max_points: int = 64, reach_hops: int | None = None):
+    """True shortest paths (by ``length``) for ``n_cars`` cars, destinations uniform over the map.
 
-    Returns ``(path_ptr[int64 N+1], path_xy[float64 P,2], origin_idx, dest_idx)``.  The path of a car is the
-    polyline of node positions origin..destination - what ``navigation.shortest_path_lines_nx`` +
-    ``models.path_decompiler`` (``navigation.py:801-841``, ``models.py:116-137``) produce on a graph without
-    edge ``geometry``: per edge the two endpoints, consecutive duplicates dropped.
+    A bounded set of Dijkstra trees (``n_sources`` roots, search radius ``reach_hops``) is shared by all cars: every
+    sub-path of a shortest path is a shortest path, so a car's route is the last ``l`` hops (``2 <= l <= max_hops``)
+    of the tree path root -> destination, for a root at least ``l`` hops away.  Origins therefore spread over the whole
+    map instead of piling up on the roots.
+
+    Returns ``(path_ptr[int64 N+1], path_xy[float64 P,2], origin_idx, dest_idx)``.  A car's polyline is the node
+    positions origin..destination - what ``navigation.shortest_path_lines_nx`` + ``models.path_decompiler``
+    (``navigation.py:801-841``, ``models.py:116-137``) produce on a graph without edge ``geometry``.
     """
     from scipy.sparse.csgraph import dijkstra
 
@@ -122,56 +126,53 @@ def make_routes(graph: SynthGraph, n_cars: int, max_hops: int = 40, n_sources: i
     n = graph.n_nodes
     m = graph.csr()
     n_sources = int(min(n_sources, n))
+    max_l = int(min(max_hops, max_points - 1, graph.nx + graph.ny - 2))
+    if reach_hops is None:
+        reach_hops = max_l + 40
     sources = rng.choice(n, size=n_sources, replace=False)
-    limit = (max_hops + 2) * graph.spacing * 1.2
-    dist, pred = dijkstra(m, directed=True, indices=sources, return_predecessors=True, limit=limit)
-    # hop distance on the grid bounds the polyline length
-    src_of_car = rng.integers(0, n_sources, size=n_cars)
-    origin = sources[src_of_car]
-    orow, ocol = origin // graph.nx, origin % graph.nx
-    hops_total = rng.integers(2, max(3, min(max_hops, max_points - 1)) + 1, size=n_cars)
-    frac = rng.random(n_cars)
-    dr = np.rint(hops_total * frac).astype(np.int64) * rng.choice([-1, 1], n_cars)
-    dc = (hops_total - np.abs(dr)) * rng.choice([-1, 1], n_cars)
-    drow = np.clip(orow + dr, 0, graph.ny - 1)
-    dcol = np.clip(ocol + dc, 0, graph.nx - 1)
-    dest = drow * graph.nx + dcol
-    same = dest == origin
-    # nudge degenerate destinations one node away (an empty route parks the car from t=0, Appendix B-15;
-    # we keep a few of those on purpose in the small configs but not here)
-    dest[same] = np.where(ocol[same] + 1 < graph.nx, origin[same] + 1, origin[same] - 1)
-    # walk predecessors dest -> origin (vectorised over cars)
-    cur = dest.copy()
-    rev = [cur.copy()]
-    alive = cur != origin
-    for _ in range(max_points + 8):
-        if not alive.any():
+    limit = reach_hops * graph.spacing * 1.25
+    _, pred = dijkstra(m, directed=True, indices=sources, return_predecessors=True, limit=limit)
+    pred = pred.astype(np.int32)
+    srow, scol = sources // graph.nx, sources % graph.nx
+
+    dest = rng.integers(0, n, size=n_cars)
+    hops = rng.integers(2, max_l + 1, size=n_cars)
+    drow, dcol = dest // graph.nx, dest % graph.nx
+    src_of_car = np.full(n_cars, -1, np.int64)
+    todo = np.arange(n_cars)
+    for rnd in range(400):
+        if len(todo) == 0:
             break
+        if rnd and rnd % 25 == 0:  # unlucky destinations (map corners far from every root): redraw them
+            dest[todo] = rng.integers(0, n, size=len(todo))
+            hops[todo] = rng.integers(2, max(3, max_l // (1 + rnd // 100)) + 1, size=len(todo))
+            drow, dcol = dest // graph.nx, dest % graph.nx
+        cand = rng.integers(0, n_sources, size=len(todo))
+        hd = np.abs(srow[cand] - drow[todo]) + np.abs(scol[cand] - dcol[todo])
+        ok = (hd >= hops[todo]) & (hd <= reach_hops - 8) & (pred[cand, dest[todo]] >= 0)
+        src_of_car[todo[ok]] = cand[ok]
+        todo = todo[~ok]
+    if len(todo):
+        raise RuntimeError("could not route %d cars; use more sources or a larger reach" % len(todo))
+    # walk `hops` predecessors from the destination towards the root (vectorised over cars)
+    chain = np.full((n_cars, max_l + 1), -1, np.int32)
+    cur = dest.astype(np.int32)
+    chain[:, 0] = cur
+    for k in range(1, max_l + 1):
+        alive = (hops >= k) & (cur != sources[src_of_car])
         nxt = pred[src_of_car, cur]
-        nxt = np.where(alive, nxt, cur)
-        unreachable = nxt < 0
-        if unreachable.any():
-            raise RuntimeError("destination outside the Dijkstra limit; raise `limit`")
-        cur = nxt
-        rev.append(np.where(alive, cur, -1))
-        alive = cur != origin
-    rev = np.stack(rev, 1)  # (N, Lmax) dest .. origin then -1 padding
-    length = (rev >= 0).sum(1)
-    # reverse each row into origin .. dest order
-    Lmax = rev.shape[1]
-    ar = np.arange(Lmax)[None, :]
+        cur = np.where(alive, nxt, cur).astype(np.int32)
+        chain[:, k] = np.where(alive, cur, -1)
+    length = (chain >= 0).sum(1)                      # points origin..dest
+    ar = np.arange(max_l + 1)[None, :]
     gather = length[:, None] - 1 - ar
     valid = gather >= 0
-    fwd = np.take_along_axis(rev, np.where(valid, gather, 0), 1)
-    # cap at max_points
-    length = np.minimum(length, max_points)
-    valid &= ar < length[:, None]
+    fwd = np.take_along_axis(chain, np.where(valid, gather, 0), 1)
     path_ptr = np.zeros(n_cars + 1, np.int64)
     np.cumsum(length, out=path_ptr[1:])
-    nodes_flat = fwd[valid]
-    path_xy = graph.node_xy[nodes_flat]
-    dest_eff = fwd[np.arange(n_cars), length - 1]
-    return path_ptr, path_xy, origin, dest_eff
+    path_xy = graph.node_xy[fwd[valid]]
+    origin = fwd[:, 0].astype(np.int64)
+    return path_ptr, path_xy, origin, dest
 
 
 def make_lights(graph: SynthGraph, prescale: int = 10, seed: int = 0):
@@ -205,3 +206,42 @@ def make_lights(graph: SynthGraph, prescale: int = 10, seed: int = 0):
     switch_time = np.round(rng.random(len(light_nodes)) * degree, 2)
     return dict(node=graph.node_ids[light_nodes], xy=graph.node_xy[light_nodes].copy(), degree=degree.astype(np.int32),
                 switch_time=switch_time, face_ptr=face_ptr, face_vec=face_vec, face_go=face_go)
+
+
+def make_city(nx_: int, ny_: int, n_cars: int, prescale: int = 10, seed: int = 0, x0: float = 551000.0,
+              y0: float = 4180000.0, max_hops: int = 40, max_points: int = 64, n_sources: int = 256,
+              stagger: bool = True):
+    """A full synthetic ``World`` (graph + routed cars + lights) of arbitrary size, same semantics as a world packed
+    from the reference's DataFrames.  With ``stagger`` each car starts at a random point of its first edge and its
+    polyline starts at that edge's far end, so co-located starts with identical routes (mutually invisible forever,
+    SURVEY Appendix B-5) do not occur.  Returns ``(world, graph)``.
+    """
+    from .state import make_world
+
+    g = SynthGraph(nx_, ny_, x0=x0, y0=y0, seed=seed)
+    path_ptr, path_xy, origin, dest = make_routes(g, n_cars, max_hops=max_hops, n_sources=n_sources, seed=seed + 1,
+                                                  max_points=max_points)
+    rng = np.random.default_rng(seed + 2)
+    start = path_ptr[:-1]
+    if stagger:
+        p0 = path_xy[start]
+        p1 = path_xy[start + 1]          # every route has >= 2 points (destination != origin)
+        frac = rng.uniform(0.0, 0.9, n_cars)[:, None]
+        pos = p0 + frac * (p1 - p0)
+        keep = np.ones(len(path_xy), bool)
+        keep[start] = False
+        path_xy = path_xy[keep]
+        path_ptr = path_ptr - np.arange(n_cars + 1)
+    else:
+        pos = path_xy[start].copy()
+    lights = make_lights(g, prescale=prescale, seed=seed + 3)
+    w = make_world(g.axis, pos, path_ptr, path_xy, g.node_xy[dest], lights)
+    return w, g
+
+
+CITY_CONFIGS = {
+    # BASELINE.json configs[1..3] (SURVEY.md §8(d)); sizes of the synthetic grid, cars, light prescale, UTM-like offset
+    "c2_manhattan_2k": dict(nx_=64, ny_=64, n_cars=2000, prescale=10, x0=583000.0, y0=4507000.0, max_hops=40),
+    "c3_sf_50k": dict(nx_=100, ny_=100, n_cars=50000, prescale=10, x0=551000.0, y0=4180000.0, max_hops=40),
+    "c4_city_1m": dict(nx_=316, ny_=316, n_cars=1000000, prescale=10, x0=551000.0, y0=4180000.0, max_hops=60),
+}
