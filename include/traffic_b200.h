@@ -114,6 +114,12 @@ int tb2_download(const tb2_sim* sim, int field, void* dst, size_t bytes, void* s
  * (replaces the bin assignment at the end of the reference initialisers, simulation.py:246-250) */
 int tb2_prepare(tb2_sim* sim, void* stream);
 
+/* Cars.update(dt, lights) alone (cars.py:61-95): one fused launch, lights untouched.  The light-face states it
+ * reads are the device-resident TB2_FACE_GO (upload them first if the caller's lights live elsewhere). */
+int tb2_cars_update(tb2_sim* sim, double dt, void* stream);
+/* TrafficLights.update(dt) alone (cars.py:123-133) */
+int tb2_lights_update(tb2_sim* sim, double dt, void* stream);
+
 /* n_steps of { Cars.update(dt, lights.state) ; TrafficLights.update(dt) } in the given order (cars.py:61-95,
  * 123-133).  Asynchronous on `stream`. */
 int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stream);

@@ -264,12 +264,20 @@ int tb2_prepare(tb2_sim* s, void* stream) {
     return TB2_OK;
 }
 
-int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream_) {
-    if (!s) return fail(TB2_ERR_INVALID, "null sim");
-    if (n_steps < 0) return fail(TB2_ERR_INVALID, "negative n_steps");
-    if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
-    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (positions were uploaded since)");
-    cudaStream_t stream = (cudaStream_t)stream_;
+}  // extern "C"
+
+namespace {
+
+// TrafficLights.update (cars.py:123-133) as its own launch
+void tick_lights(tb2_sim* s, double dt, cudaStream_t stream) {
+    launch_lights_tick(s->cfg.n_lights, dt, s->buf<double>(B_SWITCH_TIME), s->buf<int32_t>(B_FACE_PTR),
+                       s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0), s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1),
+                       s->buf<double>(s->cur_t ? B_T1 : B_T0), s->buf<double>(s->cur_t ? B_T0 : B_T1), stream);
+    s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
+}
+
+// Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch
+void step_cars(tb2_sim* s, double dt, int tick, cudaStream_t stream) {
     const size_t C2 = (size_t)2 * s->n_cells;
     StepArgs64 a{};
     fill_grid_args(s, &a);
@@ -291,33 +299,57 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
     a.cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
     a.cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
     a.switch_time = s->buf<double>(B_SWITCH_TIME);
+    a.tick = tick;
+    a.pos_in = s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0);
+    a.pos_out = s->buf<double2>(s->cur_pos ? B_POS0 : B_POS1);
+    a.cell_in = s->buf<int32_t>(s->cur_cell ? B_CELL1 : B_CELL0);
+    a.cell_out = s->buf<int32_t>(s->cur_cell ? B_CELL0 : B_CELL1);
+    int32_t* tab = s->buf<int32_t>(B_TAB);
+    a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
+    a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
+    a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
+    a.go_cur = s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0);
+    a.go_next = s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1);
+    a.t_cur = s->buf<double>(s->cur_t ? B_T1 : B_T0);
+    a.t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
+    launch_step_f64(a, stream);
+    s->launches++;
+    s->last_cell_in = s->cur_cell;
+    s->cur_pos ^= 1; s->cur_cell ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
+    if (tick) { s->cur_go ^= 1; s->cur_t ^= 1; }
+    s->steps++;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb2_lights_update(tb2_sim* s, double dt, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    tick_lights(s, dt, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_cars_update(tb2_sim* s, double dt, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_cars_update before tb2_prepare (positions were uploaded since)");
+    step_cars(s, dt, 0, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream_) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    if (n_steps < 0) return fail(TB2_ERR_INVALID, "negative n_steps");
+    if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
+    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (positions were uploaded since)");
+    cudaStream_t stream = (cudaStream_t)stream_;
     for (int32_t k = 0; k < n_steps; ++k) {
-        if (order == TB2_ORDER_LIGHTS_CARS && k == 0) {
-            // L (C L) (C L) ... C : the first tick is its own launch, the rest ride in the step kernel
-            launch_lights_tick(s->cfg.n_lights, dt, a.switch_time, a.face_ptr, s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0),
-                               s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1), s->buf<double>(s->cur_t ? B_T1 : B_T0),
-                               s->buf<double>(s->cur_t ? B_T0 : B_T1), stream);
-            s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
-        }
-        a.tick = (order == TB2_ORDER_CARS_LIGHTS) ? 1 : (k < n_steps - 1 ? 1 : 0);
-        a.pos_in = s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0);
-        a.pos_out = s->buf<double2>(s->cur_pos ? B_POS0 : B_POS1);
-        a.cell_in = s->buf<int32_t>(s->cur_cell ? B_CELL1 : B_CELL0);
-        a.cell_out = s->buf<int32_t>(s->cur_cell ? B_CELL0 : B_CELL1);
-        int32_t* tab = s->buf<int32_t>(B_TAB);
-        a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
-        a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
-        a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
-        a.go_cur = s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0);
-        a.go_next = s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1);
-        a.t_cur = s->buf<double>(s->cur_t ? B_T1 : B_T0);
-        a.t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
-        launch_step_f64(a, stream);
-        s->launches++;
-        s->last_cell_in = s->cur_cell;
-        s->cur_pos ^= 1; s->cur_cell ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
-        if (a.tick) { s->cur_go ^= 1; s->cur_t ^= 1; }
-        s->steps++;
+        // lights-first order: L (C L) (C L) ... C - the first tick is its own launch, the rest ride in the step kernel
+        if (order == TB2_ORDER_LIGHTS_CARS && k == 0) tick_lights(s, dt, stream);
+        const int tick = (order == TB2_ORDER_CARS_LIGHTS) ? 1 : (k < n_steps - 1 ? 1 : 0);
+        step_cars(s, dt, tick, stream);
     }
     CU(cudaGetLastError());
     return TB2_OK;

@@ -30,7 +30,7 @@ F64, F32 = 0, 1
 FIELD_COUNT = 21
 
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
-           "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host",
+           "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
            "tb2_launch_count", "tb2_step_count"]
 
 
@@ -86,6 +86,8 @@ def lib():
         L.tb2_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
         L.tb2_step_host.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
+        L.tb2_cars_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.tb2_lights_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.tb2_launch_count.restype = C.c_int64
         L.tb2_launch_count.argtypes = [C.c_void_p]
         L.tb2_step_count.restype = C.c_int64
@@ -218,6 +220,14 @@ class DeviceSim:
     def step(self, dt: float, n_steps: int = 1, order: int = ORDER_CARS_LIGHTS):
         with self._torch.cuda.device(self.device):
             _check(self.L.tb2_step(self.h, C.c_double(dt), C.c_int32(n_steps), C.c_int32(order), self._stream()), "tb2_step")
+
+    def cars_update(self, dt: float):
+        with self._torch.cuda.device(self.device):
+            _check(self.L.tb2_cars_update(self.h, C.c_double(dt), self._stream()), "tb2_cars_update")
+
+    def lights_update(self, dt: float):
+        with self._torch.cuda.device(self.device):
+            _check(self.L.tb2_lights_update(self.h, C.c_double(dt), self._stream()), "tb2_lights_update")
 
     def step_host(self, dt, n_steps, order, face_go_in=None, frame_out=None, face_go_out=None):
         """End-to-end call with host buffers (pinned numpy/torch memory recommended)."""
