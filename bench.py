@@ -30,12 +30,13 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-# algorithmic bytes per car-step of the fused fp64 step kernel (DESIGN.md §Kernels, table "step_f64"):
-#   reads : pos 16, route_time 8, cursor 4, path_end 4, path_eff_end 4, cell 4, view (3 polyline points) 48,
-#           cell-table entry 8, candidate position 16                                   = 112
-#   writes: pos 16, vel 16, route_time 8, d_node/d_car/d_light 24, leader 4, next cell 4,
-#           two 4-byte atomics into the next cell table 8                               = 80
-ALGO_BYTES = {"f64": 192.0}
+# algorithmic bytes per car-step of the fused fp64 step kernel (DESIGN.md "Kernels", table step_f64), for the launches
+# of a tb2_step batch that do not write the observation-only columns (all but the last of the batch):
+#   reads : pos 16, route_time 8, cursor 4, path_end 4, path_eff_end 4, cell 4, cached head point 16,
+#           cached curvature constants 16, cell-table entry 8, candidate position 16            = 96
+#   writes: pos 16, route_time 8, two 4-byte atomics into the next cell table 8                 = 32
+# (lights / faces / cell->lights CSR are O(L) << N and L2-resident: counted as 0)
+ALGO_BYTES = {"f64": 128.0}
 L2_BYTES = 126e6
 
 

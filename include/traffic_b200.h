@@ -85,7 +85,9 @@ typedef struct tb2_config {
     double speed_limit, stop_distance, free_distance, default_acceleration;
     /* TB2_F32 only: positions are stored as (x - origin_x, y - origin_y) */
     double origin_x, origin_y;
-    int32_t write_aux;   /* 1: write TB2_LEADER / TB2_CELL / distances every step (parity + facade); 0: skip LEADER */
+    int32_t write_aux;   /* 1: TB2_VEL, TB2_D_*, TB2_LEADER and TB2_CELL are valid after every tb2_cars_update and
+                          *    after the LAST step of every tb2_step batch (columns nobody can observe between the steps
+                          *    of a batch are not written); 0: never written (pure stepping) */
     int32_t reserved;
 } tb2_config;
 

@@ -96,3 +96,49 @@ def compare_step(snap, g, t, ncx, rtol, report):
             report.append("step %d: %s rel err %.3e at car %d (got %r want %r)" % (t, name, m, i, a[i], b[i]))
             ok = False
     return ok, worst
+
+
+class FakeNodes(dict):
+    pass
+
+
+class FakeGraph:
+    """Duck-typed OGraph for the facade tests: .axis and .G.nodes[node]['x'|'y'] (navigation.py:566-578)."""
+
+    def __init__(self, axis, dest_xy):
+        from types import SimpleNamespace
+        self.axis = tuple(float(a) for a in axis)
+        nodes = FakeNodes({10_000 + i: {"x": float(p[0]), "y": float(p[1])} for i, p in enumerate(dest_xy)})
+        self.G = SimpleNamespace(nodes=nodes)
+        self.fig = None
+        self.ax = SimpleNamespace(axis=lambda: self.axis)
+
+
+def frames_from_golden(g):
+    """Rebuild the reference-schema DataFrames (simulation.py:226-252, 358-378) from a golden fixture."""
+    import pandas as pd
+
+    n = len(g["pos0"])
+    ptr = g["path_ptr"]
+    cars = pd.DataFrame({
+        "object": ["car"] * n, "x": g["pos0"][:, 0], "y": g["pos0"][:, 1], "vx": 0, "vy": 0, "route-time": 0,
+        "origin": np.arange(n), "destination": 10_000 + np.arange(n),
+        "route": [[0, 1]] * n,
+        "xpath": [g["path_xy"][ptr[i]:ptr[i + 1], 0].tolist() for i in range(n)],
+        "ypath": [g["path_xy"][ptr[i]:ptr[i + 1], 1].tolist() for i in range(n)],
+        "distance-to-car": 0, "distance-to-node": 0, "distance-to-red-light": 0})
+    grid = Grid.from_axis(tuple(g["axis"]))
+    ex, ey = grid.edges()
+    cars["xbin"], cars["ybin"] = np.digitize(cars["x"], ex), np.digitize(cars["y"], ey)
+    fp = g["face_ptr"]
+    L = len(g["switch_time"])
+    lights = pd.DataFrame({
+        "object": ["light"] * L, "node": np.arange(L), "degree": np.diff(fp), "x": g["light_xy"][:, 0],
+        "y": g["light_xy"][:, 1], "switch-counter": 0, "switch-time": g["switch_time"],
+        "out-xpositions": [(g["light_xy"][i, 0] + 0.3 * g["face_vec"][fp[i]:fp[i + 1], 0]).tolist() for i in range(L)],
+        "out-ypositions": [(g["light_xy"][i, 1] + 0.3 * g["face_vec"][fp[i]:fp[i + 1], 1]).tolist() for i in range(L)],
+        "out-xvectors": [g["face_vec"][fp[i]:fp[i + 1], 0].tolist() for i in range(L)],
+        "out-yvectors": [g["face_vec"][fp[i]:fp[i + 1], 1].tolist() for i in range(L)],
+        "go-values": [g["face_go0"][fp[i]:fp[i + 1]].astype(bool) for i in range(L)],
+        "xbin": g["light_xbin"], "ybin": g["light_ybin"]})
+    return cars, lights, FakeGraph(g["axis"], g["dest_xy"])

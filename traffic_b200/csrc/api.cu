@@ -36,8 +36,9 @@ size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 // internal buffer ids (superset of tb2_field: ping-pong partners and the cell tables)
 enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
-    B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL0, B_CELL1, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
-    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_COUNT
+    B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
+    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV, B_FACE_UNIT,
+    B_COUNT
 };
 
 struct Layout {
@@ -72,7 +73,10 @@ Layout make_layout(const tb2_config& c) {
     b[B_PATH_XY] = P * 2 * R;
     b[B_DEST_XY] = N * 2 * R;
     b[B_D_NODE] = b[B_D_CAR] = b[B_D_LIGHT] = N * R;
-    b[B_CELL0] = b[B_CELL1] = N * 4;
+    b[B_CELL] = b[B_CELL_PREV] = N * 4;
+    b[B_HEAD_XY] = b[B_HEAD_CURV] = N * 2 * R;
+    b[B_PT_CURV] = P * 2 * R;
+    b[B_FACE_UNIT] = F * 2 * R;
     b[B_LEADER] = N * 4;
     b[B_TAB] = 3 * 2 * C * 4;
     b[B_LIGHT_XY] = L * 2 * R;
@@ -101,8 +105,7 @@ struct tb2_sim {
     char* arena = nullptr;
     bool owns_arena = false;
     int n_cells = 0;
-    int cur_pos = 0, cur_cell = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
-    int last_cell_in = 0;  // cell buffer that held the bins of the last executed step's start positions
+    int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
     int64_t launches = 0, steps = 0;
     double log_free_over_stop = 0.0;
@@ -130,7 +133,7 @@ int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) 
         case TB2_D_NODE: *b = B_D_NODE; *elem = R; *count = N; return 0;
         case TB2_D_CAR: *b = B_D_CAR; *elem = R; *count = N; return 0;
         case TB2_D_LIGHT: *b = B_D_LIGHT; *elem = R; *count = N; return 0;
-        case TB2_CELL: *b = s->last_cell_in ? B_CELL1 : B_CELL0; *elem = 4; *count = N; return 0;
+        case TB2_CELL: *b = B_CELL_PREV; *elem = 4; *count = N; return 0;
         case TB2_LEADER: *b = B_LEADER; *elem = 4; *count = N; return 0;
         case TB2_LIGHT_XY: *b = B_LIGHT_XY; *elem = R; *count = L * 2; return 0;
         case TB2_SWITCH_TIME: *b = B_SWITCH_TIME; *elem = 8; *count = L; return 0;
@@ -144,15 +147,41 @@ int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) 
     }
 }
 
-void fill_grid_args(const tb2_sim* s, StepArgs64* a) {
+void fill_args(const tb2_sim* s, StepArgs64* a) {
     const tb2_config& c = s->cfg;
-    a->n_cars = c.n_cars; a->n_lights = c.n_lights; a->n_cells = s->n_cells;
+    a->g.nbx = c.nbx; a->g.nby = c.nby; a->g.ncx = c.nbx + 1; a->g.n_cells = s->n_cells;
+    a->g.ex0 = c.ex0; a->g.ex1 = c.ex1; a->g.exd = c.exd; a->g.ey0 = c.ey0; a->g.ey1 = c.ey1; a->g.eyd = c.eyd;
+    a->g.inv_exd = 1.0 / c.exd; a->g.inv_eyd = 1.0 / c.eyd;
+    a->n_cars = c.n_cars; a->n_lights = c.n_lights;
     a->car_blocks = (c.n_cars + 255) / 256;
-    a->nbx = c.nbx; a->nby = c.nby; a->ncx = c.nbx + 1; a->write_aux = c.write_aux;
-    a->ex0 = c.ex0; a->ex1 = c.ex1; a->exd = c.exd; a->ey0 = c.ey0; a->ey1 = c.ey1; a->eyd = c.eyd;
     a->speed_limit = c.speed_limit; a->stop_distance = c.stop_distance; a->free_distance = c.free_distance;
     a->default_acceleration = c.default_acceleration;
     a->log_free_over_stop = s->log_free_over_stop;
+    a->vel = s->buf<double2>(B_VEL);
+    a->route_time = s->buf<double>(B_ROUTE_TIME);
+    a->cursor = s->buf<int32_t>(B_CURSOR);
+    a->path_end = s->buf<int32_t>(B_PATH_END);
+    a->path_eff_end = s->buf<int32_t>(B_PATH_EFF_END);
+    a->path_xy = s->buf<double2>(B_PATH_XY);
+    a->pt_curv = s->buf<double2>(B_PT_CURV);
+    a->dest_xy = s->buf<double2>(B_DEST_XY);
+    a->head_xy = s->buf<double2>(B_HEAD_XY);
+    a->head_curv = s->buf<double2>(B_HEAD_CURV);
+    a->d_node = s->buf<double>(B_D_NODE);
+    a->d_car = s->buf<double>(B_D_CAR);
+    a->d_light = s->buf<double>(B_D_LIGHT);
+    a->cell = s->buf<int32_t>(B_CELL);
+    a->cell_prev = s->buf<int32_t>(B_CELL_PREV);
+    a->leader = s->buf<int32_t>(B_LEADER);
+    a->light_xy = s->buf<double2>(B_LIGHT_XY);
+    a->face_ptr = s->buf<int32_t>(B_FACE_PTR);
+    a->face_vec = s->buf<double2>(B_FACE_VEC);
+    a->face_unit = s->buf<double2>(B_FACE_UNIT);
+    a->cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
+    a->cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
+    a->switch_time = s->buf<double>(B_SWITCH_TIME);
+    a->pos_in = s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0);
+    a->pos_out = s->buf<double2>(s->cur_pos ? B_POS0 : B_POS1);
 }
 
 }  // namespace
@@ -232,7 +261,8 @@ int tb2_upload(tb2_sim* s, int field, const void* src, size_t bytes, void* strea
     }
     if (bytes && !src) return fail(TB2_ERR_INVALID, "null source");
     if (bytes) CU(cudaMemcpyAsync(s->arena + s->lay.off[b], src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
-    if (field == TB2_POS) s->prepared = false;
+    if (field == TB2_POS || field == TB2_CURSOR || field == TB2_PATH_END || field == TB2_PATH_XY ||
+        field == TB2_FACE_VEC) s->prepared = false;
     return TB2_OK;
 }
 
@@ -252,13 +282,11 @@ int tb2_download(const tb2_sim* s, int field, void* dst, size_t bytes, void* str
 
 int tb2_prepare(tb2_sim* s, void* stream) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
-    StepArgs64 g{};
-    fill_grid_args(s, &g);
-    launch_prepare_f64(s->cfg.n_cars, s->n_cells, s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0),
-                       s->buf<int32_t>(s->cur_cell ? B_CELL1 : B_CELL0), s->buf<int32_t>(B_TAB), s->cur_tab, g,
-                       (cudaStream_t)stream);
-    s->launches += s->cfg.n_cars > 0 ? 2 : 1;
-    s->last_cell_in = s->cur_cell;
+    StepArgs64 a{};
+    fill_args(s, &a);
+    launch_prepare_f64(a, s->buf<double2>(B_PT_CURV), s->buf<double2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
+                       s->cur_tab, (cudaStream_t)stream);
+    s->launches += 1 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0);
     CU(cudaGetLastError());
     s->prepared = true;
     return TB2_OK;
@@ -276,34 +304,15 @@ void tick_lights(tb2_sim* s, double dt, cudaStream_t stream) {
     s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
 }
 
-// Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch
-void step_cars(tb2_sim* s, double dt, int tick, cudaStream_t stream) {
+// Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
+// aux: also write the columns nobody can observe between steps (velocity, distances, leader, start-of-step bin).
+void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
     const size_t C2 = (size_t)2 * s->n_cells;
     StepArgs64 a{};
-    fill_grid_args(s, &a);
+    fill_args(s, &a);
     a.dt = dt;
-    a.vel = s->buf<double2>(B_VEL);
-    a.route_time = s->buf<double>(B_ROUTE_TIME);
-    a.cursor = s->buf<int32_t>(B_CURSOR);
-    a.path_end = s->buf<int32_t>(B_PATH_END);
-    a.path_eff_end = s->buf<int32_t>(B_PATH_EFF_END);
-    a.path_xy = s->buf<double2>(B_PATH_XY);
-    a.dest_xy = s->buf<double2>(B_DEST_XY);
-    a.d_node = s->buf<double>(B_D_NODE);
-    a.d_car = s->buf<double>(B_D_CAR);
-    a.d_light = s->buf<double>(B_D_LIGHT);
-    a.leader = s->buf<int32_t>(B_LEADER);
-    a.light_xy = s->buf<double2>(B_LIGHT_XY);
-    a.face_ptr = s->buf<int32_t>(B_FACE_PTR);
-    a.face_vec = s->buf<double2>(B_FACE_VEC);
-    a.cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
-    a.cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
-    a.switch_time = s->buf<double>(B_SWITCH_TIME);
     a.tick = tick;
-    a.pos_in = s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0);
-    a.pos_out = s->buf<double2>(s->cur_pos ? B_POS0 : B_POS1);
-    a.cell_in = s->buf<int32_t>(s->cur_cell ? B_CELL1 : B_CELL0);
-    a.cell_out = s->buf<int32_t>(s->cur_cell ? B_CELL0 : B_CELL1);
+    a.write_aux = aux;
     int32_t* tab = s->buf<int32_t>(B_TAB);
     a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
     a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
@@ -314,8 +323,7 @@ void step_cars(tb2_sim* s, double dt, int tick, cudaStream_t stream) {
     a.t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
     launch_step_f64(a, stream);
     s->launches++;
-    s->last_cell_in = s->cur_cell;
-    s->cur_pos ^= 1; s->cur_cell ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
+    s->cur_pos ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
     if (tick) { s->cur_go ^= 1; s->cur_t ^= 1; }
     s->steps++;
 }
@@ -334,7 +342,7 @@ int tb2_lights_update(tb2_sim* s, double dt, void* stream) {
 int tb2_cars_update(tb2_sim* s, double dt, void* stream) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
     if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_cars_update before tb2_prepare (positions were uploaded since)");
-    step_cars(s, dt, 0, (cudaStream_t)stream);
+    step_cars(s, dt, 0, s->cfg.write_aux, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return TB2_OK;
 }
@@ -349,7 +357,7 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
         // lights-first order: L (C L) (C L) ... C - the first tick is its own launch, the rest ride in the step kernel
         if (order == TB2_ORDER_LIGHTS_CARS && k == 0) tick_lights(s, dt, stream);
         const int tick = (order == TB2_ORDER_CARS_LIGHTS) ? 1 : (k < n_steps - 1 ? 1 : 0);
-        step_cars(s, dt, tick, stream);
+        step_cars(s, dt, tick, (s->cfg.write_aux && k == n_steps - 1) ? 1 : 0, stream);
     }
     CU(cudaGetLastError());
     return TB2_OK;

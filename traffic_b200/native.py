@@ -17,7 +17,7 @@ import numpy as np
 from .state import World
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(_CSRC, "libtraffic_b200.so")
+LIB_PATH = os.environ.get("TB2_LIB", os.path.join(_CSRC, "libtraffic_b200.so"))  # TB2_LIB: kernel-variant experiments
 
 ABI_VERSION = 1
 ORDER_CARS_LIGHTS = 0  # test/profile_cars_update.py:29-34
