@@ -281,30 +281,29 @@ __global__ void __launch_bounds__(256, TB2_MIN_BLOCKS) step_f64_kernel(const __g
         // Both speed factors have the form log(d / den) / L on (stop, free]:
         //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den) (cached)
         //   simulation.obstacle_factor       (simulation.py:167-186): den = stop,            L = log(free/stop)
-        // so they share one code path, evaluated for (0) the curvature factor and (1) the obstacle factor.
+        // so they share one code path.  Pass 0 evaluates the factor the car actually uses (obstacle factor when it
+        // has an obstacle, curvature factor otherwise); pass 1 only runs for cars that blend both (models.weigh_factors).
         const bool c_t = d_car != 0.0, r_t = d_light != 0.0;  // Python truthiness (NaN truthy)
+        const bool obs = c_t || r_t;
+        const bool weigh = c_t && !r_t && d_car > d_node;      // simulation.py:120-126
         const double d_obs = (c_t && r_t) ? ((d_car <= d_light) ? d_car : d_light) : (c_t ? d_car : d_light);
-        double curv = 1.0, fobs = 1.0;
+        double r0 = 1.0, r1 = 1.0;
 #pragma unroll 1
         for (int it = 0; it < 2; ++it) {
-            const double d = it ? d_obs : d_node;
-            const double den = it ? a.stop_distance : hc.x;
-            const double L = it ? a.log_free_over_stop : hc.y;
-            const bool wanted = it ? (c_t || r_t) : (hc.x != 0.0);
+            const bool as_obs = (it == 0) && obs;
+            const bool wanted = (it == 0) ? (obs || hc.x != 0.0) : (weigh && hc.x != 0.0);
+            const double d = as_obs ? d_obs : d_node;
+            const double den = as_obs ? a.stop_distance : hc.x;
+            const double L = as_obs ? a.log_free_over_stop : hc.y;
             double r = 1.0;
             if (wanted) {
                 if (a.stop_distance < d && d <= a.free_distance) r = log(d / den) / L;
-                else if (it && d <= a.stop_distance) r = 0.0;
+                else if (as_obs && d <= a.stop_distance) r = 0.0;
             }
-            if (it) fobs = r; else curv = r;
+            if (it == 0) r0 = r; else r1 = r;
         }
-        double f = curv;
-        if (c_t || r_t) {
-            f = fobs;
-            // models.weigh_factors (models.py:41-66), simulation.py:120-126
-            if (c_t && !r_t && d_car > d_node)
-                f = fobs * cos(d_car / a.free_distance) + curv * sin(d_node / a.free_distance);
-        }
+        double f = r0;   // curvature factor without an obstacle, obstacle factor with one
+        if (weigh) f = r0 * cos(d_car / a.free_distance) + r1 * sin(d_node / a.free_distance);  // models.py:41-66
         f = fabs(f);
         vx = dx / d_node * a.speed_limit * f;
         vy = dy / d_node * a.speed_limit * f;
