@@ -138,7 +138,8 @@ def run_reference_arm(args):
         return
     from oracle import oracle
     cores = os.cpu_count() or 1
-    w = make_workload(args.workload, args.seed)
+    # c5_ensemble: the CPU arm advances one replica (replicas are independent and identical in cost)
+    w = make_workload("c2_manhattan_2k" if args.workload == "c5_ensemble" else args.workload, args.seed)
     dt, order = args.dt, 0
     for _ in range(args.warmup):
         oracle.run(w, dt, 1, order, threads=cores)
@@ -167,7 +168,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--workload", default="c4_city_1m")
+    ap.add_argument("--workload", default="c4_city_1m",
+                    help="c4_city_1m | c3_sf_50k | c2_manhattan_2k (one simulation per GPU) | c5_ensemble (--replicas "
+                         "rollouts of the 2k-car world, sharded over the GPUs)")
+    ap.add_argument("--replicas", type=int, default=4096, help="c5_ensemble: total number of replicas")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--dt", type=float, default=1e-3)
     ap.add_argument("--seed", type=int, default=0)
@@ -200,9 +204,19 @@ def main():
         torch.cuda.synchronize()
 
     dt, order = args.dt, native.ORDER_CARS_LIGHTS  # the profile script's order
-    w = make_workload(args.workload, args.seed + rank)  # every rank: an independent replica (different seed)
-    sim = native.DeviceSim(w, write_aux=True)
-    N = w.n_cars
+    ens = None
+    if args.workload == "c5_ensemble":
+        # BASELINE configs[4]: R rollouts of the 2k-car world with randomised light timings, round-robin over the ranks
+        from traffic_b200 import ensemble
+        w = make_workload("c2_manhattan_2k", args.seed)
+        ids = ensemble.shard(args.replicas, world, rank)
+        ens = ensemble.Ensemble(w, ids, agent_car=17, seed=args.seed, write_aux=True)  # learn.py:14: agent = car 17
+        sim = ens.sim
+        N = w.n_cars * len(ids)
+    else:
+        w = make_workload(args.workload, args.seed + rank)  # every rank: an independent replica (different seed)
+        sim = native.DeviceSim(w, write_aux=True)
+        N = w.n_cars
 
     # ---- device-resident throughput ----
     sim.step(dt, args.warmup, order)
@@ -234,7 +248,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call ----
     k = max(1, min(args.frame_every, args.steps))
     frames = max(1, args.steps // k)
-    frame = torch.empty((N, 2), dtype=torch.float64).pin_memory()
+    frame = torch.empty((N, 2), dtype=torch.float64).pin_memory()  # all local replicas' positions
     go_in = torch.from_numpy(sim.download(native.FACE_GO).copy()).pin_memory()
     go_out = torch.empty_like(go_in).pin_memory()
     sim.step_host(dt, k, order, go_in, frame, go_out)  # warm
@@ -263,6 +277,13 @@ def main():
     else:
         allstats = stats
     allstats = allstats.cpu().numpy().reshape(-1, 2)
+    rollout = None
+    if ens is not None:
+        from traffic_b200 import ensemble
+        res = ensemble.gather_results(ens.results(sim.step_count), args.replicas)  # [R,4] trip_time, steps, done, id
+        rollout = {"replicas": int(args.replicas), "arrived": int(np.nansum(res[:, 2])),
+                   "mean_trip_time_arrived": float(np.nanmean(np.where(res[:, 2] > 0, res[:, 0], np.nan)))
+                   if np.nansum(res[:, 2]) > 0 else None}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -280,8 +301,10 @@ def main():
         line = {
             "metric": "vehicle-updates/sec", "value": value, "unit": "vehicle-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "cars_per_gpu": N, "lights": w.n_lights, "faces": w.n_faces,
+            "higher_is_better": True, "scaling": "strong" if ens is not None else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "cars_per_gpu": N, "replicas_per_gpu": sim.n_replicas,
+                       "lights": w.n_lights, "faces": w.n_faces,
                        "path_points": int(len(w.path_xy)), "cells": w.grid.n_cells, "dt": dt,
                        "order": "cars_then_lights", "replicas": world, "parallelism": "replica-per-gpu",
                        "l2": "working set %.0f MB per step > %.0f MB L2, no explicit flush" % (ws / 1e6, L2_BYTES / 1e6),
@@ -296,12 +319,14 @@ def main():
             "replica_stats": {"mean_route_time": [float(x) for x in allstats[:, 0]],
                               "parked_fraction": [float(x) for x in allstats[:, 1]]},
         }
+        if rollout is not None:
+            line["rollout"] = rollout
         if not args.no_cpu_baseline:
             v, s_, t_ = cpu_port_updates_per_s(w, dt, order, args.cpu_budget, threads=1)
             line["cpu_baseline"] = {"value": v, "unit": "vehicle-updates/s", "cores": 1, "kind": "port",
                                     "sample": "%d steps of the same %d-car workload (%.1f s), C oracle port, 1 thread; "
                                               "the unmodified Python reference runs 300-450 updates/s on one core"
-                                              % (s_, N, t_)}
+                                              % (s_, w.n_cars, t_)}
         if not args.no_small and args.workload != "c2_manhattan_2k":
             w2 = make_workload("c2_manhattan_2k", args.seed)
             s2 = native.DeviceSim(w2)

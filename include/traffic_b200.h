@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TB2_ABI_VERSION 1
+#define TB2_ABI_VERSION 2
 
 /* order of the two reference calls inside one step */
 #define TB2_ORDER_CARS_LIGHTS 0 /* test/profile_cars_update.py:29-34 */
@@ -67,7 +67,11 @@ typedef enum tb2_field {
     TB2_CELL_LIGHT_PTR = 18, /* [C+1] i32  static cell -> lights CSR (lights in DataFrame order)           */
     TB2_CELL_LIGHT_IDX = 19, /* [LC]  i32                                                                  */
     TB2_LIGHTS_TIME = 20, /* [1]    f64  TrafficLights.time_elapsed (cars.py:117,130)                     */
-    TB2_FIELD_COUNT = 21
+    /* replica ensembles (environment.Env rollouts, environment.py:97-173): per replica */
+    TB2_DONE = 21,        /* [R]    i32  1 once the agent car satisfied FrontView.end_of_route (navigation.py:113-128) */
+    TB2_TRIP_TIME = 22,   /* [R]    f64  the agent's 'route-time' when it arrived (environment.py:126)        */
+    TB2_TRIP_STEP = 23,   /* [R]    i32  number of simulation steps executed before arrival                   */
+    TB2_FIELD_COUNT = 24
 } tb2_field;
 
 typedef struct tb2_config {
@@ -89,6 +93,12 @@ typedef struct tb2_config {
                           *    after the LAST step of every tb2_step batch (columns nobody can observe between the steps
                           *    of a batch are not written); 0: never written (pure stepping) */
     int32_t reserved;
+    /* Replica ensemble: n_replicas independent copies of the same world (same graph, routes and light geometry) with
+     * their own car state, light timings (TB2_SWITCH_TIME [R*L]) and face states (TB2_FACE_GO [R*F]), advanced by
+     * the same launches.  n_cars / n_lights / n_faces are PER REPLICA; per-car fields hold R*n_cars elements, replica
+     * r at [r*n_cars, (r+1)*n_cars); TB2_LEADER holds indices local to the replica.  1 = a single simulation. */
+    int32_t n_replicas;
+    int32_t agent_car;   /* car whose arrival ends a rollout (learn.py:14 uses 17); -1: no agent tracking */
 } tb2_config;
 
 typedef struct tb2_sim tb2_sim;

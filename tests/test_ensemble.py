@@ -1,0 +1,123 @@
+"""Replica ensembles: sharding + gather over a world_size-2 gloo group on CPU, the reward restatement, and (GPU) the
+batched-replica kernel path against one oracle run per replica."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from traffic_b200 import ensemble
+
+
+def test_shard_round_robin_covers_everything():
+    for R, W in ((4096, 8), (10, 4), (3, 2), (1, 2)):
+        seen = np.concatenate([ensemble.shard(R, W, r) for r in range(W)])
+        assert sorted(seen.tolist()) == list(range(R))
+
+
+def test_reward_matches_env_step_rules():
+    # environment.py:129-150: fewer than 5 recorded trips -> no bonus; first episode -> reward 0
+    assert ensemble.reward([3.0], (0, 40), 1e-3) == (0.0, False)
+    assert ensemble.reward([3.0, 2.5], (1, 40), 1e-3) == (0.5, False)
+    assert ensemble.reward([3.0, 3.5], (1, 40), 1e-3) == (0.0, False)
+    r, done = ensemble.reward([3.0, 2.9, 2.8, 2.7, 2.6], (4, 40), 1e-3)  # new minimum within 5*dt of the minimum
+    assert done and abs(r - (0.1 + 10.0)) < 1e-12
+    r, done = ensemble.reward([3.0, 2.0, 2.8, 2.7, 2.9], (4, 40), 1e-3)
+    assert not done and r == 0.0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world_size, port, n_replicas, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    ids = ensemble.shard(n_replicas, world_size, rank)
+    # fake rollout results: trip_time = 10 + id, steps = 100 * id, done = id % 2
+    local = np.stack([10.0 + ids, 100.0 * ids, (ids % 2).astype(float), ids.astype(float)], 1)
+    out = ensemble.gather_results(local, n_replicas)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_replicas", [7, 16])
+def test_gather_results_gloo_world_size_2(n_replicas):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_replicas, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = np.arange(n_replicas, dtype=float)
+    want = np.stack([10.0 + ids, 100.0 * ids, ids % 2, ids], 1)
+    for _, out in outs:
+        assert np.array_equal(out, want)
+
+
+def test_gather_results_single_process():
+    ids = np.array([2, 0, 1])
+    local = np.stack([ids + 0.5, ids * 2.0, np.ones(3), ids.astype(float)], 1)
+    out = ensemble.gather_results(local, 3)
+    assert np.array_equal(out[:, 3], [0, 1, 2]) and np.array_equal(out[:, 0], [0.5, 1.5, 2.5])
+
+
+@pytest.mark.gpu
+def test_ensemble_matches_one_oracle_run_per_replica():
+    from oracle import oracle
+    from traffic_b200 import native, synth
+
+    w0, _ = synth.make_city(nx_=32, ny_=32, n_cars=1500, prescale=3, seed=21, max_hops=6)
+    R, dt, steps = 6, 1e-3, 400
+    lens = w0.path_end - w0.path_start
+    # an agent that does arrive: a short route whose last edge runs mostly along x (a car parks when it "crosses" its
+    # last point - a 5.7 m x 42 m window at these coordinates - but end_of_route wants 5 m on both axes, Appendix B-9)
+    last = w0.path_xy[w0.path_end - 1] - np.where((lens >= 2)[:, None], w0.path_xy[np.maximum(w0.path_end - 2, 0)], w0.pos)
+    ok = (lens >= 1) & (lens <= 3) & (np.abs(last[:, 0]) > 1.5 * np.abs(last[:, 1]))
+    agent = None
+    for cand in np.flatnonzero(ok)[:40]:
+        wt = w0.copy()
+        for k in range(steps):
+            d = wt.dest_xy[cand] - wt.pos[cand]
+            if np.isclose(0, d[0], atol=5) and np.isclose(0, d[1], atol=5):
+                agent = int(cand)
+                break
+            oracle.run(wt, dt, 1, oracle.ORDER_LIGHTS_CARS)
+        if agent is not None:
+            break
+    assert agent is not None, "no arriving agent candidate in the test world"
+    ens = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
+    res = ens.rollout(dt, max_steps=steps, chunk=steps)
+    assert ens.sim.step_count == steps
+    for r in range(R):
+        wc = w0.copy()
+        wc.switch_time = ens.switch_time[r].copy()
+        trip = None
+        for k in range(steps):
+            # Env.simulation_step: test end_of_route before stepping (environment.py:161-171)
+            d = wc.dest_xy[agent] - wc.pos[agent]
+            if trip is None and np.isclose(0, d[0], atol=5) and np.isclose(0, d[1], atol=5):
+                trip = (wc.route_time[agent], k)
+            oracle.run(wc, dt, 1, oracle.ORDER_LIGHTS_CARS)
+        wg = ens.sim.download_world(w0.copy(), replica=r)
+        for f in ("cursor", "cell", "leader", "face_go"):
+            assert np.array_equal(getattr(wg, f), getattr(wc, f)), "replica %d field %s" % (r, f)
+        assert np.allclose(wg.pos, wc.pos, rtol=1e-12, atol=0)
+        if trip is None:
+            assert res[r, 2] == 0
+        else:
+            assert res[r, 2] == 1 and res[r, 1] == trip[1] and abs(res[r, 0] - trip[0]) < 1e-12
+    assert res[:, 2].sum() >= 1, "test world: no agent arrived, pick a shorter route"
+    assert len({tuple(ens.switch_time[r]) for r in range(R)}) == R

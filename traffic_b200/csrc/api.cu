@@ -37,7 +37,7 @@ size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
     B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
-    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV, B_FACE_UNIT,
+    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV, B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP,
     B_COUNT
 };
 
@@ -57,11 +57,17 @@ bool config_ok(const tb2_config* c, std::string* why) {
     if (c->nbx < 0 || c->nby < 0) { *why = "negative bin count"; return false; }
     if ((int64_t)(c->nbx + 1) * (c->nby + 1) > (int64_t)1 << 28) { *why = "too many cells"; return false; }
     if (c->n_path_points >= ((int64_t)1 << 31)) { *why = "more than 2^31 path points"; return false; }
+    if (c->n_replicas < 1) { *why = "n_replicas must be >= 1"; return false; }
+    if ((int64_t)c->n_replicas * c->n_cars >= ((int64_t)1 << 31) - 1) { *why = "more than 2^31 cars"; return false; }
+    if ((int64_t)c->n_replicas * (c->nbx + 1) * (c->nby + 1) > (int64_t)1 << 29) { *why = "too many cells x replicas"; return false; }
+    if (c->agent_car >= c->n_cars) { *why = "agent_car out of range"; return false; }
     return true;
 }
 
 Layout make_layout(const tb2_config& c) {
-    const size_t N = (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
+    // per-car / per-replica buffers hold all replicas back to back; geometry (paths, light positions, faces) is shared
+    const size_t Rep = (size_t)c.n_replicas;
+    const size_t N = Rep * (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
     const size_t C = (size_t)(c.nbx + 1) * (size_t)(c.nby + 1), LC = (size_t)c.n_cell_lights;
     const size_t R = sizeof(double);
     Layout l{};
@@ -78,15 +84,17 @@ Layout make_layout(const tb2_config& c) {
     b[B_PT_CURV] = P * 2 * R;
     b[B_FACE_UNIT] = F * 2 * R;
     b[B_LEADER] = N * 4;
-    b[B_TAB] = 3 * 2 * C * 4;
+    b[B_TAB] = 3 * 2 * C * Rep * 4;
     b[B_LIGHT_XY] = L * 2 * R;
-    b[B_SWITCH_TIME] = L * 8;
+    b[B_SWITCH_TIME] = Rep * L * 8;
     b[B_FACE_PTR] = (L + 1) * 4;
     b[B_FACE_VEC] = F * 2 * R;
-    b[B_GO0] = b[B_GO1] = F;
+    b[B_GO0] = b[B_GO1] = Rep * F;
     b[B_CELL_LIGHT_PTR] = (C + 1) * 4;
     b[B_CELL_LIGHT_IDX] = LC * 4;
     b[B_T0] = b[B_T1] = 8;
+    b[B_DONE] = b[B_TRIP_STEP] = Rep * 4;
+    b[B_TRIP_TIME] = Rep * 8;
     size_t off = 0;
     for (int i = 0; i < B_COUNT; ++i) {
         l.off[i] = off;
@@ -119,9 +127,13 @@ namespace {
 // map a public field to (internal buffer, element bytes, element count)
 int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) {
     const tb2_config& c = s->cfg;
-    const size_t N = (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
+    const size_t Rep = (size_t)c.n_replicas;
+    const size_t N = Rep * (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
     const size_t R = sizeof(double);
     switch (field) {
+        case TB2_DONE: *b = B_DONE; *elem = 4; *count = Rep; return 0;
+        case TB2_TRIP_TIME: *b = B_TRIP_TIME; *elem = 8; *count = Rep; return 0;
+        case TB2_TRIP_STEP: *b = B_TRIP_STEP; *elem = 4; *count = Rep; return 0;
         case TB2_POS: *b = s->cur_pos ? B_POS1 : B_POS0; *elem = R; *count = N * 2; return 0;
         case TB2_VEL: *b = B_VEL; *elem = R; *count = N * 2; return 0;
         case TB2_ROUTE_TIME: *b = B_ROUTE_TIME; *elem = R; *count = N; return 0;
@@ -136,10 +148,10 @@ int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) 
         case TB2_CELL: *b = B_CELL_PREV; *elem = 4; *count = N; return 0;
         case TB2_LEADER: *b = B_LEADER; *elem = 4; *count = N; return 0;
         case TB2_LIGHT_XY: *b = B_LIGHT_XY; *elem = R; *count = L * 2; return 0;
-        case TB2_SWITCH_TIME: *b = B_SWITCH_TIME; *elem = 8; *count = L; return 0;
+        case TB2_SWITCH_TIME: *b = B_SWITCH_TIME; *elem = 8; *count = Rep * L; return 0;
         case TB2_FACE_PTR: *b = B_FACE_PTR; *elem = 4; *count = L + 1; return 0;
         case TB2_FACE_VEC: *b = B_FACE_VEC; *elem = R; *count = F * 2; return 0;
-        case TB2_FACE_GO: *b = s->cur_go ? B_GO1 : B_GO0; *elem = 1; *count = F; return 0;
+        case TB2_FACE_GO: *b = s->cur_go ? B_GO1 : B_GO0; *elem = 1; *count = Rep * F; return 0;
         case TB2_CELL_LIGHT_PTR: *b = B_CELL_LIGHT_PTR; *elem = 4; *count = (size_t)s->n_cells + 1; return 0;
         case TB2_CELL_LIGHT_IDX: *b = B_CELL_LIGHT_IDX; *elem = 4; *count = (size_t)c.n_cell_lights; return 0;
         case TB2_LIGHTS_TIME: *b = s->cur_t ? B_T1 : B_T0; *elem = 8; *count = 1; return 0;
@@ -152,8 +164,16 @@ void fill_args(const tb2_sim* s, StepArgs64* a) {
     a->g.nbx = c.nbx; a->g.nby = c.nby; a->g.ncx = c.nbx + 1; a->g.n_cells = s->n_cells;
     a->g.ex0 = c.ex0; a->g.ex1 = c.ex1; a->g.exd = c.exd; a->g.ey0 = c.ey0; a->g.ey1 = c.ey1; a->g.eyd = c.eyd;
     a->g.inv_exd = 1.0 / c.exd; a->g.inv_eyd = 1.0 / c.eyd;
-    a->n_cars = c.n_cars; a->n_lights = c.n_lights;
-    a->car_blocks = (c.n_cars + 255) / 256;
+    a->n_replicas = c.n_replicas; a->cars_per_replica = c.n_cars > 0 ? c.n_cars : 1;
+    a->lights_per_replica = c.n_lights > 0 ? c.n_lights : 1; a->faces_per_replica = c.n_faces;
+    a->n_cars = c.n_replicas * c.n_cars; a->n_lights = c.n_replicas * c.n_lights;
+    a->car_blocks = (a->n_cars + 255) / 256;
+    a->agent_car = c.agent_car; a->step_index = (int32_t)s->steps;
+    a->done = s->buf<int32_t>(B_DONE); a->trip_time = s->buf<double>(B_TRIP_TIME); a->trip_step = s->buf<int32_t>(B_TRIP_STEP);
+    a->go_cur = s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0);
+    a->go_next = s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1);
+    a->t_cur = s->buf<double>(s->cur_t ? B_T1 : B_T0);
+    a->t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
     a->speed_limit = c.speed_limit; a->stop_distance = c.stop_distance; a->free_distance = c.free_distance;
     a->default_acceleration = c.default_acceleration;
     a->log_free_over_stop = s->log_free_over_stop;
@@ -284,9 +304,13 @@ int tb2_prepare(tb2_sim* s, void* stream) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
     StepArgs64 a{};
     fill_args(s, &a);
+    CU(cudaMemsetAsync(s->buf<char>(B_DONE), 0, s->lay.bytes[B_DONE], (cudaStream_t)stream));
+    CU(cudaMemsetAsync(s->buf<char>(B_TRIP_TIME), 0, s->lay.bytes[B_TRIP_TIME], (cudaStream_t)stream));
+    CU(cudaMemsetAsync(s->buf<char>(B_TRIP_STEP), 0, s->lay.bytes[B_TRIP_STEP], (cudaStream_t)stream));
     launch_prepare_f64(a, s->buf<double2>(B_PT_CURV), s->buf<double2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
                        s->cur_tab, (cudaStream_t)stream);
     s->launches += 1 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0);
+    s->steps = 0;
     CU(cudaGetLastError());
     s->prepared = true;
     return TB2_OK;
@@ -298,16 +322,17 @@ namespace {
 
 // TrafficLights.update (cars.py:123-133) as its own launch
 void tick_lights(tb2_sim* s, double dt, cudaStream_t stream) {
-    launch_lights_tick(s->cfg.n_lights, dt, s->buf<double>(B_SWITCH_TIME), s->buf<int32_t>(B_FACE_PTR),
-                       s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0), s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1),
-                       s->buf<double>(s->cur_t ? B_T1 : B_T0), s->buf<double>(s->cur_t ? B_T0 : B_T1), stream);
+    StepArgs64 a{};
+    fill_args(s, &a);
+    a.dt = dt;
+    launch_lights_tick(a, stream);
     s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
 }
 
 // Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
 // aux: also write the columns nobody can observe between steps (velocity, distances, leader, start-of-step bin).
 void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
-    const size_t C2 = (size_t)2 * s->n_cells;
+    const size_t C2 = (size_t)2 * s->n_cells * s->cfg.n_replicas;
     StepArgs64 a{};
     fill_args(s, &a);
     a.dt = dt;
@@ -317,10 +342,6 @@ void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
     a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
     a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
     a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
-    a.go_cur = s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0);
-    a.go_next = s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1);
-    a.t_cur = s->buf<double>(s->cur_t ? B_T1 : B_T0);
-    a.t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
     launch_step_f64(a, stream);
     s->launches++;
     s->cur_pos ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
@@ -366,7 +387,7 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
 int tb2_step_host(tb2_sim* s, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
                   void* frame_xy_out, uint8_t* face_go_out, void* stream) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
-    const size_t F = (size_t)s->cfg.n_faces, N = (size_t)s->cfg.n_cars;
+    const size_t F = (size_t)s->cfg.n_faces * s->cfg.n_replicas, N = (size_t)s->cfg.n_cars * s->cfg.n_replicas;
     if (face_go_in) if (int rc = tb2_upload(s, TB2_FACE_GO, face_go_in, F, stream)) return rc;
     if (int rc = tb2_step(s, dt, n_steps, order, stream)) return rc;
     if (frame_xy_out) if (int rc = tb2_download(s, TB2_POS, frame_xy_out, N * 2 * sizeof(double), stream)) return rc;

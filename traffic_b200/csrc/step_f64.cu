@@ -177,12 +177,12 @@ __device__ __noinline__ bool antiparallel_exact(double cvx, double cvy, double2 
     if (c > kCosT + 1.0e-6) return false;
     return isclose_(kPi, acos(c), 1.0e-5, 0.1);
 }
-__device__ __forceinline__ bool red_face_ahead(const StepArgs64& a, int l, double cvx, double cvy) {
+__device__ __forceinline__ bool red_face_ahead(const StepArgs64& a, int l, int fbase, double cvx, double cvy) {
     const float fx = __double2float_rn(cvx), fy = __double2float_rn(cvy);
     const float inv = rsqrtf(fx * fx + fy * fy);
     bool found = false;
     for (int f = a.face_ptr[l]; f < a.face_ptr[l + 1] && !found; ++f) {
-        if (a.go_cur[f]) continue;
+        if (a.go_cur[fbase + f]) continue;
         const double2 fu = a.face_unit[f];
         const float c = (fx * __double2float_rn(fu.x) + fy * __double2float_rn(fu.y)) * inv;
         if (c < (float)kCosT - 1.0e-4f) found = true;
@@ -191,18 +191,21 @@ __device__ __forceinline__ bool red_face_ahead(const StepArgs64& a, int l, doubl
     return found;
 }
 
-__device__ __forceinline__ void lights_tick_body(int l, int n_lights, double dt, const double* __restrict__ switch_time,
+// TrafficLights.update  (cars.py:130-133); lg runs over replicas x lights, geometry (face_ptr) is shared
+__device__ __forceinline__ void lights_tick_body(int lg, int n_lights_total, int lights_per_replica, int faces_per_replica,
+                                                 double dt, const double* __restrict__ switch_time,
                                                  const int32_t* __restrict__ face_ptr, const uint8_t* __restrict__ go_cur,
                                                  uint8_t* __restrict__ go_next, const double* t_cur, double* t_next) {
-    // TrafficLights.update  (cars.py:130-133)
     const double t = *t_cur + dt;
-    if (l == 0) *t_next = t;
-    if (l >= n_lights) return;
-    const double sw = switch_time[l];
+    if (lg == 0) *t_next = t;
+    if (lg >= n_lights_total) return;
+    const int rep = lg / lights_per_replica, l = lg - rep * lights_per_replica;
+    const int fbase = rep * faces_per_replica;
+    const double sw = switch_time[lg];
     double r = fmod(t, sw);                       // numpy float remainder
     if (r != 0.0 && ((sw < 0.0) != (r < 0.0))) r += sw;
     const bool s = isclose_(0.0, r, 1.0e-4, 1.0e-8);
-    for (int f = face_ptr[l]; f < face_ptr[l + 1]; ++f) go_next[f] = s ? (uint8_t)!go_cur[f] : go_cur[f];
+    for (int f = face_ptr[l]; f < face_ptr[l + 1]; ++f) go_next[fbase + f] = s ? (uint8_t)!go_cur[fbase + f] : go_cur[fbase + f];
 }
 
 __device__ __forceinline__ void table_insert(int32_t* tab, int cell, int i) {
@@ -211,17 +214,23 @@ __device__ __forceinline__ void table_insert(int32_t* tab, int cell, int i) {
     if (loser != TB2_EMPTY) atomicMin(&tab[2 * cell + 1], loser);
 }
 
-template <bool AUX>
+// AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell tables / face states, agent
+// arrival bookkeeping); a single simulation compiles these out.
+template <bool AUX, bool ENS>
 __global__ void __launch_bounds__(256, TB2_MIN_BLOCKS) step_f64_kernel(const __grid_constant__ StepArgs64 a) {
     if ((int)blockIdx.x >= a.car_blocks) {
         const int l = ((int)blockIdx.x - a.car_blocks) * 256 + (int)threadIdx.x;
-        lights_tick_body(l, a.n_lights, a.dt, a.switch_time, a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next);
+        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt, a.switch_time, a.face_ptr,
+                         a.go_cur, a.go_next, a.t_cur, a.t_next);
         return;
     }
     const int i = (int)blockIdx.x * 256 + (int)threadIdx.x;
     // reset the table that the launch after next will fill
-    for (int k = i; k < 2 * a.g.n_cells; k += a.car_blocks * 256) a.tab_clear[k] = TB2_EMPTY;
+    for (int k = i; k < 2 * a.g.n_cells * a.n_replicas; k += a.car_blocks * 256) a.tab_clear[k] = TB2_EMPTY;
     if (i >= a.n_cars) return;
+    // replica of this car (1 for a single simulation): offsets into the per-replica cell tables and face states
+    const int rep = ENS ? i / a.cars_per_replica : 0;
+    const int cbase = rep * a.g.n_cells, fbase = rep * a.faces_per_replica, ibase = rep * a.cars_per_replica;
 
     // ---- independent loads first ----
     const double2 p = a.pos_in[i];
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(256, TB2_MIN_BLOCKS) step_f64_kernel(const __g
     const double2 hc = a.head_curv[i];
     const double rt = a.route_time[i];
     // ---- dependent on the bin ----
-    const int2 m = a.tab_cur[c];
+    const int2 m = a.tab_cur[cbase + c];
     const int lb = a.cell_light_ptr[c], le = a.cell_light_ptr[c + 1];
 
     const double x = p.x, y = p.y;
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(256, TB2_MIN_BLOCKS) step_f64_kernel(const __g
             const double2 lp = a.light_xy[l];
             if (on_axis(ax, 1, lp.x) && on_axis(ay, 1, lp.y)) {
                 const double cvx = lp.x - x, cvy = lp.y - y;
-                if (red_face_ahead(a, l, cvx, cvy)) { d_light = norm2(cvx, cvy); break; }
+                if (red_face_ahead(a, l, fbase, cvx, cvy)) { d_light = norm2(cvx, cvy); break; }
             } else { d_light = 0.0; break; }
         }
     }
@@ -328,13 +337,23 @@ __global__ void __launch_bounds__(256, TB2_MIN_BLOCKS) step_f64_kernel(const __g
         a.d_node[i] = d_node;
         a.d_car[i] = d_car;
         a.d_light[i] = d_light;
-        a.leader[i] = lead;
+        a.leader[i] = lead >= 0 ? lead - ibase : -1;
         a.cell_prev[i] = c;
     }
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of(a.g, xn, yn);
     if (cn != c) a.cell[i] = cn;
-    table_insert(a.tab_next, cn, i);
+    table_insert(a.tab_next, cbase + cn, i);
+    // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
+    // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
+    if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
+        const double2 d = a.dest_xy[i];
+        if (isclose_(0.0, d.x - x, 1.0e-5, 5.0) && isclose_(0.0, d.y - y, 1.0e-5, 5.0)) {
+            a.done[rep] = 1;
+            a.trip_time[rep] = rt;
+            a.trip_step[rep] = a.step_index;
+        }
+    }
 }
 
 // prepare, pass 1: curvature constants of every polyline point still ahead of its car
@@ -355,7 +374,7 @@ __global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgs 
                                                            const double2* __restrict__ path_xy,
                                                            const double2* __restrict__ pt_curv, double2* head_xy,
                                                            double2* head_curv, int32_t* cell, int32_t* cell_prev,
-                                                           int32_t* tab) {
+                                                           int32_t* tab, int cars_per_replica) {
     const int i = (int)blockIdx.x * 256 + (int)threadIdx.x;
     if (i >= n_cars) return;
     const int cur = cursor[i];
@@ -367,7 +386,7 @@ __global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgs 
     const int cn = cell_of(g, p.x, p.y);
     cell[i] = cn;
     cell_prev[i] = cn;
-    table_insert(tab, cn, i);
+    table_insert(tab, (i / cars_per_replica) * g.n_cells + cn, i);
 }
 
 // prepare: unit vectors of the light faces (models.unit_vector, models.py:74-76)
@@ -384,11 +403,13 @@ __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
 }
 
-__global__ void __launch_bounds__(256) lights_tick_kernel(int n_lights, double dt, const double* switch_time,
+__global__ void __launch_bounds__(256) lights_tick_kernel(int n_lights, int lights_per_replica, int faces_per_replica,
+                                                          double dt, const double* switch_time,
                                                           const int32_t* face_ptr, const uint8_t* go_cur, uint8_t* go_next,
                                                           const double* t_cur, double* t_next) {
     const int l = (int)blockIdx.x * 256 + (int)threadIdx.x;
-    lights_tick_body(l, n_lights, dt, switch_time, face_ptr, go_cur, go_next, t_cur, t_next);
+    lights_tick_body(l, n_lights, lights_per_replica, faces_per_replica, dt, switch_time, face_ptr, go_cur, go_next, t_cur,
+                     t_next);
 }
 
 }  // namespace
@@ -397,13 +418,19 @@ void launch_step_f64(const StepArgs64& a, cudaStream_t stream) {
     const int light_blocks = a.tick ? ((a.n_lights + 255) / 256 > 0 ? (a.n_lights + 255) / 256 : 1) : 0;
     const int grid = a.car_blocks + light_blocks;
     if (grid <= 0) return;
-    if (a.write_aux) step_f64_kernel<true><<<grid, 256, 0, stream>>>(a);
-    else step_f64_kernel<false><<<grid, 256, 0, stream>>>(a);
+    const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
+    if (ens) {
+        if (a.write_aux) step_f64_kernel<true, true><<<grid, 256, 0, stream>>>(a);
+        else step_f64_kernel<false, true><<<grid, 256, 0, stream>>>(a);
+    } else {
+        if (a.write_aux) step_f64_kernel<true, false><<<grid, 256, 0, stream>>>(a);
+        else step_f64_kernel<false, false><<<grid, 256, 0, stream>>>(a);
+    }
 }
 
 void launch_prepare_f64(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3,
                         int cur_table, cudaStream_t stream) {
-    const size_t n = (size_t)6 * a.g.n_cells;
+    const size_t n = (size_t)6 * a.g.n_cells * a.n_replicas;
     const size_t blocks = (n + 255) / 256;
     fill_i32_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(tab3, n, TB2_EMPTY);
     if (n_faces > 0) prepare_faces_kernel<<<(n_faces + 255) / 256, 256, 0, stream>>>(n_faces, a.face_vec, face_unit);
@@ -412,13 +439,12 @@ void launch_prepare_f64(const StepArgs64& a, double2* pt_curv, double2* face_uni
                                                                             pt_curv, a.stop_distance, a.free_distance);
         prepare_cars_kernel<<<(a.n_cars + 255) / 256, 256, 0, stream>>>(
             a.n_cars, a.g, a.pos_in, a.cursor, a.path_end, a.path_xy, pt_curv, a.head_xy, a.head_curv, a.cell,
-            a.cell_prev, tab3 + (size_t)2 * a.g.n_cells * cur_table);
+            a.cell_prev, tab3 + (size_t)2 * a.g.n_cells * a.n_replicas * cur_table, a.cars_per_replica);
     }
 }
 
-void launch_lights_tick(int n_lights, double dt, const double* switch_time, const int32_t* face_ptr,
-                        const uint8_t* go_cur, uint8_t* go_next, const double* t_cur, double* t_next,
-                        cudaStream_t stream) {
-    const int blocks = (n_lights + 255) / 256 > 0 ? (n_lights + 255) / 256 : 1;
-    lights_tick_kernel<<<blocks, 256, 0, stream>>>(n_lights, dt, switch_time, face_ptr, go_cur, go_next, t_cur, t_next);
+void launch_lights_tick(const StepArgs64& a, cudaStream_t stream) {
+    const int blocks = (a.n_lights + 255) / 256 > 0 ? (a.n_lights + 255) / 256 : 1;
+    lights_tick_kernel<<<blocks, 256, 0, stream>>>(a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt,
+                                                   a.switch_time, a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next);
 }

@@ -13,7 +13,9 @@ struct GridArgs {
 
 struct StepArgs64 {
     GridArgs g;
-    int32_t n_cars, n_lights, car_blocks, write_aux;
+    int32_t n_cars, n_lights, car_blocks, write_aux;   // n_cars / n_lights: totals over all replicas
+    int32_t n_replicas, cars_per_replica, lights_per_replica, faces_per_replica;
+    int32_t agent_car, step_index;
     double speed_limit, stop_distance, free_distance, default_acceleration;
     double log_free_over_stop;  // host libm log(free/stop), simulation.py:180
     double dt;
@@ -54,6 +56,10 @@ struct StepArgs64 {
     uint8_t* go_next;
     const double* t_cur;
     double* t_next;
+    // replica-ensemble bookkeeping (environment.py:120-126, 154-173)
+    int32_t* done;
+    double* trip_time;
+    int32_t* trip_step;
 };
 
 void launch_step_f64(const StepArgs64& a, cudaStream_t stream);
@@ -61,6 +67,4 @@ void launch_step_f64(const StepArgs64& a, cudaStream_t stream);
 // head point + constants, bins, and the cell table `cur_table` of the three in tab3 (all three are reset).
 void launch_prepare_f64(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3,
                         int cur_table, cudaStream_t stream);
-void launch_lights_tick(int n_lights, double dt, const double* switch_time, const int32_t* face_ptr,
-                        const uint8_t* go_cur, uint8_t* go_next, const double* t_cur, double* t_next,
-                        cudaStream_t stream);
+void launch_lights_tick(const StepArgs64& a, cudaStream_t stream);

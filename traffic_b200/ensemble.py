@@ -1,0 +1,120 @@
+"""Replica ensembles: many independent rollouts of the same world (same graph, routes, light geometry) that differ in
+their light timings - the parallel axis of ``learn.py`` / ``environment.Env`` (one RL "step" is a whole traffic rollout,
+``environment.py:97-152``) and of randomised light-timing sweeps.
+
+* ``Ensemble`` batches R replicas into ONE device simulation: the step kernel offsets the per-cell car table and the
+  light-face states by the replica index, so a launch advances all replicas; the agent's arrival
+  (``FrontView.end_of_route``, ``navigation.py:113-128``, tested before every step as in ``Env.simulation_step``,
+  ``environment.py:154-173``) is recorded on the device (``DONE`` / ``TRIP_TIME`` / ``TRIP_STEP``), no per-step host sync.
+* ``shard`` / ``gather_results`` split the replicas over ranks (one process per GPU) and collect the per-replica results
+  with a single ``all_gather`` (NCCL on GPUs, gloo in the CPU tests); there is no data-path collective.
+* ``reward`` restates the reward bookkeeping of ``Env.step`` (``environment.py:126-150``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import native
+from .state import World
+
+
+def shard(n_replicas: int, world_size: int, rank: int):
+    """Round-robin assignment replica -> rank (balances the rollout-length tail)."""
+    return np.arange(rank, n_replicas, world_size, dtype=np.int64)
+
+
+def random_switch_times(world: World, n_replicas: int, seed: int):
+    """Per-replica light timings: ``round(U(0,1) * degree, 2)`` as ``models.determine_traffic_light_timer``
+    (``models.py:31-38``); replica r uses generator stream ``seed + r`` so shards are reproducible on any rank."""
+    degree = np.diff(world.face_ptr).astype(np.float64)
+    out = np.empty((n_replicas, world.n_lights), np.float64)
+    for r in range(n_replicas):
+        out[r] = np.round(np.random.default_rng(seed + r).random(world.n_lights) * degree, 2)
+    return out
+
+
+def reward(route_times, num, dt, high=10.0, thresh=5):
+    """``Env.step`` reward for the episode whose trip time was just appended to ``route_times``
+    (``environment.py:126-150``); ``num`` = (episode index, total)."""
+    route_times = list(route_times)
+    if len(route_times) < thresh:
+        bonus, done = 0.0, False
+    elif np.isclose(0, route_times[-1] - np.min(route_times), atol=5 * dt).all():
+        bonus, done = high, True
+    else:
+        bonus, done = 0.0, False
+    if num[0] < 1:
+        r = 0.0
+    else:
+        delta = route_times[num[0] - 1] - route_times[num[0]] + bonus
+        r = delta if delta > 0 else 0.0
+    return r, done
+
+
+class Ensemble:
+    """R replicas of ``world`` on one GPU.  ``replica_ids`` are the global ids of the replicas this rank owns."""
+
+    def __init__(self, world: World, replica_ids, agent_car: int, seed: int = 0, switch_time=None, device=None,
+                 write_aux: bool = False):
+        self.world = world
+        self.replica_ids = np.asarray(replica_ids, np.int64)
+        R = len(self.replica_ids)
+        if R < 1:
+            raise ValueError("an ensemble shard needs at least one replica")
+        if switch_time is None:
+            all_sw = random_switch_times(world, int(self.replica_ids.max()) + 1, seed)
+            switch_time = all_sw[self.replica_ids]
+        self.switch_time = np.ascontiguousarray(switch_time, np.float64).reshape(R, world.n_lights)
+        self.sim = native.DeviceSim(world, write_aux=write_aux, device=device, n_replicas=R, agent_car=agent_car,
+                                    switch_time=self.switch_time)
+        self.agent_car = agent_car
+
+    def rollout(self, dt: float, max_steps: int, chunk: int = 500, order: int = native.ORDER_LIGHTS_CARS):
+        """Advance until every replica's agent has arrived or ``max_steps`` (the reference loop has no cap and may
+        spin forever).  Returns float64 ``[R, 4]``: trip_time, steps, done, replica id."""
+        steps = 0
+        done = None
+        while steps < max_steps:
+            n = min(chunk, max_steps - steps)
+            self.sim.step(dt, n, order)
+            steps += n
+            done = self.sim.tensor(native.DONE)
+            if bool((done != 0).all().item()):   # one 4-byte-per-replica readback per chunk
+                break
+        return self.results(steps)
+
+    def results(self, steps_run: int):
+        done = self.sim.download(native.DONE)
+        trip_time = self.sim.download(native.TRIP_TIME)
+        trip_step = self.sim.download(native.TRIP_STEP)
+        if (done == 0).any():   # not arrived: report the current route time and the steps run so far
+            rt = self.sim.download(native.ROUTE_TIME).reshape(len(done), -1)[:, self.agent_car]
+            trip_time = np.where(done != 0, trip_time, rt)
+            trip_step = np.where(done != 0, trip_step, steps_run)
+        return np.stack([trip_time, trip_step.astype(np.float64), done.astype(np.float64),
+                         self.replica_ids.astype(np.float64)], 1)
+
+
+def gather_results(local: np.ndarray, n_replicas: int, group=None, device=None):
+    """all_gather of the per-replica result rows (NCCL over NVLink on GPUs, gloo on CPU).  Shards may differ in length
+    by one (round-robin), so rows are padded to ceil(R / world) and re-assembled by replica id.  Returns ``[R, 4]``."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        out = np.full((n_replicas, local.shape[1]), np.nan)
+        out[local[:, 3].astype(np.int64)] = local
+        return out
+    world_size = dist.get_world_size(group)
+    rows = -(-n_replicas // world_size)
+    pad = np.full((rows, local.shape[1]), -1.0)
+    pad[:len(local)] = local
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    t = torch.from_numpy(pad).to(dev)
+    allt = torch.empty((world_size * rows, local.shape[1]), dtype=t.dtype, device=dev)
+    dist.all_gather_into_tensor(allt, t, group=group)
+    allr = allt.cpu().numpy()
+    allr = allr[allr[:, 3] >= 0]
+    out = np.full((n_replicas, local.shape[1]), np.nan)
+    out[allr[:, 3].astype(np.int64)] = allr
+    return out

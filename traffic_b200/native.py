@@ -19,15 +19,16 @@ from .state import World
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.environ.get("TB2_LIB", os.path.join(_CSRC, "libtraffic_b200.so"))  # TB2_LIB: kernel-variant experiments
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ORDER_CARS_LIGHTS = 0  # test/profile_cars_update.py:29-34
 ORDER_LIGHTS_CARS = 1  # animate.py:63-64, environment.py:167-168
 F64, F32 = 0, 1
 
 # tb2_field
 (POS, VEL, ROUTE_TIME, CURSOR, PATH_END, PATH_EFF_END, PATH_XY, DEST_XY, D_NODE, D_CAR, D_LIGHT, CELL, LEADER,
- LIGHT_XY, SWITCH_TIME, FACE_PTR, FACE_VEC, FACE_GO, CELL_LIGHT_PTR, CELL_LIGHT_IDX, LIGHTS_TIME) = range(21)
-FIELD_COUNT = 21
+ LIGHT_XY, SWITCH_TIME, FACE_PTR, FACE_VEC, FACE_GO, CELL_LIGHT_PTR, CELL_LIGHT_IDX, LIGHTS_TIME,
+ DONE, TRIP_TIME, TRIP_STEP) = range(24)
+FIELD_COUNT = 24
 
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
            "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
@@ -44,7 +45,8 @@ class Tb2Config(C.Structure):
                 ("speed_limit", C.c_double), ("stop_distance", C.c_double), ("free_distance", C.c_double),
                 ("default_acceleration", C.c_double),
                 ("origin_x", C.c_double), ("origin_y", C.c_double),
-                ("write_aux", C.c_int32), ("reserved", C.c_int32)]
+                ("write_aux", C.c_int32), ("reserved", C.c_int32),
+                ("n_replicas", C.c_int32), ("agent_car", C.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -103,26 +105,31 @@ def _check(rc: int, what: str):
         raise NativeError("%s failed (status %d): %s" % (what, rc, lib().tb2_last_error().decode()))
 
 
-def config_of(w: World, precision: int = F64, write_aux: bool = True) -> Tb2Config:
+def config_of(w: World, precision: int = F64, write_aux: bool = True, n_replicas: int = 1, agent_car: int = -1) -> Tb2Config:
+    """``w`` describes ONE replica; per-car arrays of an ensemble are tiled by the caller (``traffic_b200.ensemble``)."""
     g, p = w.grid, w.params
     return Tb2Config(ABI_VERSION, precision, w.n_cars, w.n_lights, w.n_faces, len(w.cell_light_idx), len(w.path_xy),
                      g.nbx, g.nby, g.ex[0], g.ex[1], g.ex[2], g.ey[0], g.ey[1], g.ey[2],
                      p["speed_limit"], p["stop_distance"], p["free_distance"], p["default_acceleration"],
-                     g.axis[0], g.axis[2], 1 if write_aux else 0, 0)
+                     g.axis[0], g.axis[2], 1 if write_aux else 0, 0, n_replicas, agent_car)
 
 
 _NP_OF_FIELD = {POS: np.float64, VEL: np.float64, ROUTE_TIME: np.float64, CURSOR: np.int32, PATH_END: np.int32,
                 PATH_EFF_END: np.int32, PATH_XY: np.float64, DEST_XY: np.float64, D_NODE: np.float64,
                 D_CAR: np.float64, D_LIGHT: np.float64, CELL: np.int32, LEADER: np.int32, LIGHT_XY: np.float64,
                 SWITCH_TIME: np.float64, FACE_PTR: np.int32, FACE_VEC: np.float64, FACE_GO: np.uint8,
-                CELL_LIGHT_PTR: np.int32, CELL_LIGHT_IDX: np.int32, LIGHTS_TIME: np.float64}
+                CELL_LIGHT_PTR: np.int32, CELL_LIGHT_IDX: np.int32, LIGHTS_TIME: np.float64,
+                DONE: np.int32, TRIP_TIME: np.float64, TRIP_STEP: np.int32}
 _REAL_FIELDS = (POS, VEL, ROUTE_TIME, PATH_XY, DEST_XY, D_NODE, D_CAR, D_LIGHT, LIGHT_XY, FACE_VEC)
 
 
 class DeviceSim:
     """One simulation resident on one GPU.  ``step`` is asynchronous on the current torch stream."""
 
-    def __init__(self, world: World, precision: int = F64, write_aux: bool = True, device=None):
+    def __init__(self, world: World, precision: int = F64, write_aux: bool = True, device=None,
+                 n_replicas: int = 1, agent_car: int = -1, switch_time=None, face_go=None):
+        """``world`` describes one replica.  With ``n_replicas`` > 1 the car state is tiled and ``switch_time``
+        ``[R, L]`` / ``face_go`` ``[R, F]`` may give every replica its own light timings (default: the world's)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -131,7 +138,9 @@ class DeviceSim:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.L = lib()
         self.precision = precision
-        self.cfg = config_of(world, precision, write_aux)
+        self.cfg = config_of(world, precision, write_aux, n_replicas, agent_car)
+        self.n_replicas = int(n_replicas)
+        self._switch_time, self._face_go = switch_time, face_go
         self.n_cars, self.n_lights, self.n_faces = world.n_cars, world.n_lights, world.n_faces
         self.origin = np.array([world.grid.axis[0], world.grid.axis[2]], np.float64)
         nbytes = self.L.tb2_arena_bytes(C.byref(self.cfg))
@@ -193,24 +202,29 @@ class DeviceSim:
         return xy if self.precision == F64 else xy - self.origin
 
     def upload_world(self, w: World):
+        R = self.n_replicas
+
+        def tile(a):  # replicas back to back
+            return a if R == 1 else np.tile(a, (R,) + (1,) * (a.ndim - 1))
+
         with self._torch.cuda.device(self.device):
-            self.upload(POS, self._rel(w.pos))
-            self.upload(VEL, w.vel)
-            self.upload(ROUTE_TIME, w.route_time)
-            self.upload(CURSOR, w.cursor)
-            self.upload(PATH_END, w.path_end)
-            self.upload(PATH_EFF_END, w.path_eff_end)
+            self.upload(POS, tile(self._rel(w.pos)))
+            self.upload(VEL, tile(w.vel))
+            self.upload(ROUTE_TIME, tile(w.route_time))
+            self.upload(CURSOR, tile(w.cursor))
+            self.upload(PATH_END, tile(w.path_end))
+            self.upload(PATH_EFF_END, tile(w.path_eff_end))
             self.upload(PATH_XY, self._rel(w.path_xy))
-            self.upload(DEST_XY, self._rel(w.dest_xy))
-            self.upload(D_NODE, w.d_node)
-            self.upload(D_CAR, w.d_car)
-            self.upload(D_LIGHT, w.d_light)
-            self.upload(LEADER, w.leader)
+            self.upload(DEST_XY, tile(self._rel(w.dest_xy)))
+            self.upload(D_NODE, tile(w.d_node))
+            self.upload(D_CAR, tile(w.d_car))
+            self.upload(D_LIGHT, tile(w.d_light))
+            self.upload(LEADER, tile(w.leader))
             self.upload(LIGHT_XY, self._rel(w.light_xy))
-            self.upload(SWITCH_TIME, w.switch_time)
+            self.upload(SWITCH_TIME, tile(w.switch_time) if self._switch_time is None else np.asarray(self._switch_time, np.float64).reshape(-1))
             self.upload(FACE_PTR, w.face_ptr)
             self.upload(FACE_VEC, w.face_vec)
-            self.upload(FACE_GO, w.face_go)
+            self.upload(FACE_GO, tile(w.face_go) if self._face_go is None else np.asarray(self._face_go, np.uint8).reshape(-1))
             self.upload(CELL_LIGHT_PTR, w.cell_light_ptr)
             self.upload(CELL_LIGHT_IDX, w.cell_light_idx)
             self.upload(LIGHTS_TIME, np.array([w.lights_time], np.float64))
@@ -237,8 +251,10 @@ class DeviceSim:
             _check(self.L.tb2_step_host(self.h, C.c_double(dt), C.c_int32(n_steps), C.c_int32(order), p(face_go_in),
                                         p(frame_out), p(face_go_out), self._stream()), "tb2_step_host")
 
-    def download_world(self, w: World) -> World:
-        """Refresh the mutable fields of ``w`` from the device."""
+    def download_world(self, w: World, replica: int = 0) -> World:
+        """Refresh the mutable fields of ``w`` from the device (of one replica when this is an ensemble)."""
+        if self.n_replicas > 1:
+            return self._download_replica(w, replica)
         pos = self.download(POS).reshape(-1, 2).astype(np.float64)
         w.pos = pos if self.precision == F64 else pos + self.origin
         w.vel = self.download(VEL).reshape(-1, 2).astype(np.float64)
@@ -250,6 +266,23 @@ class DeviceSim:
         w.cell = self.download(CELL)
         w.leader = self.download(LEADER)
         w.face_go = self.download(FACE_GO)
+        w.lights_time = float(self.download(LIGHTS_TIME)[0])
+        return w
+
+    def _download_replica(self, w: World, r: int) -> World:
+        N, F = self.n_cars, self.n_faces
+        cs, fs = slice(r * N, (r + 1) * N), slice(r * F, (r + 1) * F)
+        pos = self.download(POS).reshape(-1, 2)[cs].astype(np.float64)
+        w.pos = pos if self.precision == F64 else pos + self.origin
+        w.vel = self.download(VEL).reshape(-1, 2)[cs].astype(np.float64)
+        w.route_time = self.download(ROUTE_TIME)[cs].astype(np.float64)
+        w.cursor = self.download(CURSOR)[cs].copy()
+        w.d_node = self.download(D_NODE)[cs].astype(np.float64)
+        w.d_car = self.download(D_CAR)[cs].astype(np.float64)
+        w.d_light = self.download(D_LIGHT)[cs].astype(np.float64)
+        w.cell = self.download(CELL)[cs].copy()
+        w.leader = self.download(LEADER)[cs].copy()
+        w.face_go = self.download(FACE_GO)[fs].copy()
         w.lights_time = float(self.download(LIGHTS_TIME)[0])
         return w
 
