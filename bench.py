@@ -30,13 +30,23 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+# stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version there) go to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 # algorithmic bytes per car-step of the fused fp64 step kernel (DESIGN.md "Kernels", table step_f64), for the launches
 # of a tb2_step batch that do not write the observation-only columns (all but the last of the batch):
 #   reads : pos 16, route_time 8, cursor 4, path_end 4, path_eff_end 4, cell 4, cached head point 16,
 #           cached curvature constants 16, cell-table entry 8, candidate position 16            = 96
 #   writes: pos 16, route_time 8, two 4-byte atomics into the next cell table 8                 = 32
 # (lights / faces / cell->lights CSR are O(L) << N and L2-resident: counted as 0)
-ALGO_BYTES = {"f64": 128.0}
+# fp32 throughput mode: the same fields at half the width for reals: reads 8+4+4+4+4+4+8+8+8+8 = 60, writes 8+4+8 = 20
+ALGO_BYTES = {"f64": 128.0, "f32": 80.0}
 L2_BYTES = 126e6
 
 
@@ -110,6 +120,8 @@ def make_workload(name, seed):
     from traffic_b200 import synth
     cfg = dict(synth.CITY_CONFIGS[name])
     cfg["seed"] = seed
+    if os.environ.get("TB2_SPATIAL_ORDER") == "1":   # experiment: cars numbered in bin order at t=0
+        cfg["spatial_order"] = True
     w, _ = synth.make_city(**cfg)
     return w
 
@@ -160,7 +172,7 @@ def run_reference_arm(args):
             "note": "C port of the reference algorithm (oracle/traffic_oracle.c, pinned bit-exact to the reference's "
                     "golden vectors); the unmodified Python reference measured 300-450 vehicle-updates/s on one core "
                     "(tests/golden/*.npz ref_updates_per_s)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -172,6 +184,8 @@ def main():
                     help="c4_city_1m | c3_sf_50k | c2_manhattan_2k (one simulation per GPU) | c5_ensemble (--replicas "
                          "rollouts of the 2k-car world, sharded over the GPUs)")
     ap.add_argument("--replicas", type=int, default=4096, help="c5_ensemble: total number of replicas")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f64: parity mode (reference arithmetic, bit-exact discrete outputs); f32: throughput mode")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--dt", type=float, default=1e-3)
     ap.add_argument("--seed", type=int, default=0)
@@ -204,18 +218,20 @@ def main():
         torch.cuda.synchronize()
 
     dt, order = args.dt, native.ORDER_CARS_LIGHTS  # the profile script's order
+    prec = native.F64 if args.precision == "f64" else native.F32
+    real_bytes = 8 if prec == native.F64 else 4
     ens = None
     if args.workload == "c5_ensemble":
         # BASELINE configs[4]: R rollouts of the 2k-car world with randomised light timings, round-robin over the ranks
         from traffic_b200 import ensemble
         w = make_workload("c2_manhattan_2k", args.seed)
         ids = ensemble.shard(args.replicas, world, rank)
-        ens = ensemble.Ensemble(w, ids, agent_car=17, seed=args.seed, write_aux=True)  # learn.py:14: agent = car 17
+        ens = ensemble.Ensemble(w, ids, agent_car=17, seed=args.seed, write_aux=True, precision=prec)  # learn.py:14
         sim = ens.sim
         N = w.n_cars * len(ids)
     else:
         w = make_workload(args.workload, args.seed + rank)  # every rank: an independent replica (different seed)
-        sim = native.DeviceSim(w, write_aux=True)
+        sim = native.DeviceSim(w, precision=prec, write_aux=True)
         N = w.n_cars
 
     # ---- device-resident throughput ----
@@ -248,7 +264,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call ----
     k = max(1, min(args.frame_every, args.steps))
     frames = max(1, args.steps // k)
-    frame = torch.empty((N, 2), dtype=torch.float64).pin_memory()  # all local replicas' positions
+    frame = torch.empty((N, 2), dtype=torch.float64 if prec == native.F64 else torch.float32).pin_memory()
     go_in = torch.from_numpy(sim.download(native.FACE_GO).copy()).pin_memory()
     go_out = torch.empty_like(go_in).pin_memory()
     sim.step_host(dt, k, order, go_in, frame, go_out)  # warm
@@ -264,7 +280,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = float(cars_total.item()) * frames * k / float(te.item())
     h2d = go_in.numel() / k
-    d2h = (frame.numel() * 8 + go_out.numel()) / k
+    d2h = (frame.numel() * real_bytes + go_out.numel()) / k
 
     # ---- replica statistics gathered over NCCL (the only collective on this path) ----
     rt = sim.tensor(native.ROUTE_TIME)
@@ -288,13 +304,13 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         kernel_us = ms / launches * 1e3 if launches else float("nan")
-        algo = ALGO_BYTES["f64"] * N
+        algo = ALGO_BYTES[args.precision] * N
         achieved = algo / (kernel_us * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(REPO, "profiles", "traffic_bytes.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload + ":f64")
+                traffic = json.load(open(tp)).get(args.workload + ":" + args.precision)
             except Exception:
                 traffic = None
         ws = N * 136 + min(len(w.path_xy) * 16, N * 64)
@@ -302,7 +318,7 @@ def main():
             "metric": "vehicle-updates/sec", "value": value, "unit": "vehicle-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong" if ens is not None else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": args.workload, "cars_per_gpu": N, "replicas_per_gpu": sim.n_replicas,
                        "lights": w.n_lights, "faces": w.n_faces,
                        "path_points": int(len(w.path_xy)), "cells": w.grid.n_cells, "dt": dt,
@@ -310,8 +326,9 @@ def main():
                        "l2": "working set %.0f MB per step > %.0f MB L2, no explicit flush" % (ws / 1e6, L2_BYTES / 1e6),
                        "frame_every_k_steps": k},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "step_f64_kernel", "kernel_us": kernel_us,
-                         "algorithmic_bytes_per_car_step": ALGO_BYTES["f64"], "peak_source": peak_src},
+                         "traffic": traffic, "kernel": "step_kernel<%s>" % ("double" if prec == native.F64 else "float"),
+                         "kernel_us": kernel_us, "algorithmic_bytes_per_car_step": ALGO_BYTES[args.precision],
+                         "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": "vehicle-updates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "frames": frames, "steps_per_frame": k},
             "gpu_launches": int(launches),
@@ -329,7 +346,7 @@ def main():
                                               % (s_, w.n_cars, t_)}
         if not args.no_small and args.workload != "c2_manhattan_2k":
             w2 = make_workload("c2_manhattan_2k", args.seed)
-            s2 = native.DeviceSim(w2)
+            s2 = native.DeviceSim(w2, precision=prec)
             s2.step(dt, 200, order)
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,7 +358,7 @@ def main():
             line["also"] = {"workload": "c2_manhattan_2k", "cars": w2.n_cars, "steps": 2000,
                             "value": w2.n_cars * 2000 / (ms2 * 1e-3), "unit": "vehicle-updates/s",
                             "us_per_step": ms2 / 2000 * 1e3}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,5 +1,6 @@
 // C ABI of libtraffic_b200.so (declared in include/traffic_b200.h): arena carving, uploads/downloads, and the
-// launch sequence of a simulation step.  Host-side only; the kernels live in step_f64.cu / step_f32.cu.
+// launch sequence of a simulation step.  Host-side only; the kernels live in step_kernel.cuh (instantiated for fp64 in
+// step_f64.cu and for fp32 in step_f32.cu).
 #include "../../include/traffic_b200.h"
 
 #include <cuda_runtime.h>
@@ -9,8 +10,9 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 
-#include "step_f64.cuh"
+#include "step_args.cuh"
 
 namespace {
 
@@ -33,12 +35,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 constexpr size_t kAlign = 256;
 size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
-// internal buffer ids (superset of tb2_field: ping-pong partners and the cell tables)
+// internal buffer ids (superset of tb2_field: ping-pong partners, caches and the cell tables)
 enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
     B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
-    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV, B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP,
-    B_COUNT
+    B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV,
+    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_LIGHTS, B_COUNT
 };
 
 struct Layout {
@@ -50,7 +52,7 @@ struct Layout {
 bool config_ok(const tb2_config* c, std::string* why) {
     if (!c) { *why = "null config"; return false; }
     if (c->abi_version != TB2_ABI_VERSION) { *why = "abi_version mismatch"; return false; }
-    if (c->precision != TB2_F64) { *why = "unsupported precision (only TB2_F64 is built into this library)"; return false; }
+    if (c->precision != TB2_F64 && c->precision != TB2_F32) { *why = "precision must be TB2_F64 or TB2_F32"; return false; }
     if (c->n_cars < 0 || c->n_lights < 0 || c->n_faces < 0 || c->n_cell_lights < 0 || c->n_path_points < 0) {
         *why = "negative size"; return false;
     }
@@ -69,7 +71,7 @@ Layout make_layout(const tb2_config& c) {
     const size_t Rep = (size_t)c.n_replicas;
     const size_t N = Rep * (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
     const size_t C = (size_t)(c.nbx + 1) * (size_t)(c.nby + 1), LC = (size_t)c.n_cell_lights;
-    const size_t R = sizeof(double);
+    const size_t R = c.precision == TB2_F64 ? sizeof(double) : sizeof(float);
     Layout l{};
     size_t b[B_COUNT];
     b[B_POS0] = b[B_POS1] = N * 2 * R;
@@ -95,6 +97,7 @@ Layout make_layout(const tb2_config& c) {
     b[B_T0] = b[B_T1] = 8;
     b[B_DONE] = b[B_TRIP_STEP] = Rep * 4;
     b[B_TRIP_TIME] = Rep * 8;
+    b[B_CELL_LIGHTS] = C * 32;
     size_t off = 0;
     for (int i = 0; i < B_COUNT; ++i) {
         l.off[i] = off;
@@ -120,6 +123,7 @@ struct tb2_sim {
 
     template <typename T>
     T* buf(int b) const { return reinterpret_cast<T*>(arena + lay.off[b]); }
+    size_t real_bytes() const { return cfg.precision == TB2_F64 ? sizeof(double) : sizeof(float); }
 };
 
 namespace {
@@ -129,7 +133,7 @@ int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) 
     const tb2_config& c = s->cfg;
     const size_t Rep = (size_t)c.n_replicas;
     const size_t N = Rep * (size_t)c.n_cars, L = (size_t)c.n_lights, F = (size_t)c.n_faces, P = (size_t)c.n_path_points;
-    const size_t R = sizeof(double);
+    const size_t R = s->real_bytes();
     switch (field) {
         case TB2_DONE: *b = B_DONE; *elem = 4; *count = Rep; return 0;
         case TB2_TRIP_TIME: *b = B_TRIP_TIME; *elem = 8; *count = Rep; return 0;
@@ -159,49 +163,96 @@ int field_buf(const tb2_sim* s, int field, int* b, size_t* elem, size_t* count) 
     }
 }
 
-void fill_args(const tb2_sim* s, StepArgs64* a) {
+template <typename R>
+void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
+    using R2 = typename real2<R>::type;
     const tb2_config& c = s->cfg;
+    // float mode stores coordinates relative to the origin, so the bin edges shift by the same amount
+    const double ox = std::is_same<R, float>::value ? c.origin_x : 0.0;
+    const double oy = std::is_same<R, float>::value ? c.origin_y : 0.0;
     a->g.nbx = c.nbx; a->g.nby = c.nby; a->g.ncx = c.nbx + 1; a->g.n_cells = s->n_cells;
-    a->g.ex0 = c.ex0; a->g.ex1 = c.ex1; a->g.exd = c.exd; a->g.ey0 = c.ey0; a->g.ey1 = c.ey1; a->g.eyd = c.eyd;
-    a->g.inv_exd = 1.0 / c.exd; a->g.inv_eyd = 1.0 / c.eyd;
+    a->g.ex0 = (R)(c.ex0 - ox); a->g.ex1 = (R)(c.ex1 - ox); a->g.exd = (R)c.exd;
+    a->g.ey0 = (R)(c.ey0 - oy); a->g.ey1 = (R)(c.ey1 - oy); a->g.eyd = (R)c.eyd;
+    a->g.inv_exd = (R)(1.0 / c.exd); a->g.inv_eyd = (R)(1.0 / c.eyd);
+    a->origin_x = (R)ox; a->origin_y = (R)oy;
     a->n_replicas = c.n_replicas; a->cars_per_replica = c.n_cars > 0 ? c.n_cars : 1;
     a->lights_per_replica = c.n_lights > 0 ? c.n_lights : 1; a->faces_per_replica = c.n_faces;
     a->n_cars = c.n_replicas * c.n_cars; a->n_lights = c.n_replicas * c.n_lights;
-    a->car_blocks = (a->n_cars + 255) / 256;
+    a->car_blocks = (a->n_cars + step_block_threads() - 1) / step_block_threads();
     a->agent_car = c.agent_car; a->step_index = (int32_t)s->steps;
-    a->done = s->buf<int32_t>(B_DONE); a->trip_time = s->buf<double>(B_TRIP_TIME); a->trip_step = s->buf<int32_t>(B_TRIP_STEP);
+    a->speed_limit = (R)c.speed_limit; a->stop_distance = (R)c.stop_distance; a->free_distance = (R)c.free_distance;
+    a->default_acceleration = (R)c.default_acceleration;
+    a->log_free_over_stop = (R)s->log_free_over_stop;
+    a->vel = s->buf<R2>(B_VEL);
+    a->route_time = s->buf<R>(B_ROUTE_TIME);
+    a->cursor = s->buf<int32_t>(B_CURSOR);
+    a->path_end = s->buf<int32_t>(B_PATH_END);
+    a->path_eff_end = s->buf<int32_t>(B_PATH_EFF_END);
+    a->path_xy = s->buf<R2>(B_PATH_XY);
+    a->pt_curv = s->buf<R2>(B_PT_CURV);
+    a->dest_xy = s->buf<R2>(B_DEST_XY);
+    a->head_xy = s->buf<R2>(B_HEAD_XY);
+    a->head_curv = s->buf<R2>(B_HEAD_CURV);
+    a->d_node = s->buf<R>(B_D_NODE);
+    a->d_car = s->buf<R>(B_D_CAR);
+    a->d_light = s->buf<R>(B_D_LIGHT);
+    a->cell = s->buf<int32_t>(B_CELL);
+    a->cell_prev = s->buf<int32_t>(B_CELL_PREV);
+    a->leader = s->buf<int32_t>(B_LEADER);
+    a->light_xy = s->buf<R2>(B_LIGHT_XY);
+    a->face_ptr = s->buf<int32_t>(B_FACE_PTR);
+    a->face_vec = s->buf<R2>(B_FACE_VEC);
+    a->face_unit = s->buf<R2>(B_FACE_UNIT);
+    a->cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
+    a->cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
+    a->cell_lights = s->buf<CellLightsT<R>>(B_CELL_LIGHTS);
+    a->switch_time = s->buf<double>(B_SWITCH_TIME);
+    a->pos_in = s->buf<R2>(s->cur_pos ? B_POS1 : B_POS0);
+    a->pos_out = s->buf<R2>(s->cur_pos ? B_POS0 : B_POS1);
     a->go_cur = s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0);
     a->go_next = s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1);
     a->t_cur = s->buf<double>(s->cur_t ? B_T1 : B_T0);
     a->t_next = s->buf<double>(s->cur_t ? B_T0 : B_T1);
-    a->speed_limit = c.speed_limit; a->stop_distance = c.stop_distance; a->free_distance = c.free_distance;
-    a->default_acceleration = c.default_acceleration;
-    a->log_free_over_stop = s->log_free_over_stop;
-    a->vel = s->buf<double2>(B_VEL);
-    a->route_time = s->buf<double>(B_ROUTE_TIME);
-    a->cursor = s->buf<int32_t>(B_CURSOR);
-    a->path_end = s->buf<int32_t>(B_PATH_END);
-    a->path_eff_end = s->buf<int32_t>(B_PATH_EFF_END);
-    a->path_xy = s->buf<double2>(B_PATH_XY);
-    a->pt_curv = s->buf<double2>(B_PT_CURV);
-    a->dest_xy = s->buf<double2>(B_DEST_XY);
-    a->head_xy = s->buf<double2>(B_HEAD_XY);
-    a->head_curv = s->buf<double2>(B_HEAD_CURV);
-    a->d_node = s->buf<double>(B_D_NODE);
-    a->d_car = s->buf<double>(B_D_CAR);
-    a->d_light = s->buf<double>(B_D_LIGHT);
-    a->cell = s->buf<int32_t>(B_CELL);
-    a->cell_prev = s->buf<int32_t>(B_CELL_PREV);
-    a->leader = s->buf<int32_t>(B_LEADER);
-    a->light_xy = s->buf<double2>(B_LIGHT_XY);
-    a->face_ptr = s->buf<int32_t>(B_FACE_PTR);
-    a->face_vec = s->buf<double2>(B_FACE_VEC);
-    a->face_unit = s->buf<double2>(B_FACE_UNIT);
-    a->cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
-    a->cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
-    a->switch_time = s->buf<double>(B_SWITCH_TIME);
-    a->pos_in = s->buf<double2>(s->cur_pos ? B_POS1 : B_POS0);
-    a->pos_out = s->buf<double2>(s->cur_pos ? B_POS0 : B_POS1);
+    a->done = s->buf<int32_t>(B_DONE);
+    a->trip_time = s->buf<double>(B_TRIP_TIME);
+    a->trip_step = s->buf<int32_t>(B_TRIP_STEP);
+}
+
+// TrafficLights.update (cars.py:123-133) as its own launch
+void tick_lights(tb2_sim* s, double dt, cudaStream_t stream) {
+    const tb2_config& c = s->cfg;
+    launch_lights_tick(c.n_replicas * c.n_lights, c.n_lights > 0 ? c.n_lights : 1, c.n_faces, dt,
+                       s->buf<double>(B_SWITCH_TIME), s->buf<int32_t>(B_FACE_PTR),
+                       s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0), s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1),
+                       s->buf<double>(s->cur_t ? B_T1 : B_T0), s->buf<double>(s->cur_t ? B_T0 : B_T1), stream);
+    s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
+}
+
+template <typename R>
+void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
+    const size_t C2 = (size_t)2 * s->n_cells * s->cfg.n_replicas;
+    StepArgsT<R> a{};
+    fill_args<R>(s, &a);
+    a.dt = (R)dt;
+    a.dt64 = dt;
+    a.tick = tick;
+    a.write_aux = aux;
+    int32_t* tab = s->buf<int32_t>(B_TAB);
+    a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
+    a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
+    a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
+    launch_step(a, stream);
+}
+
+// Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
+// aux: also write the columns nobody can observe between steps (velocity, distances, leader, start-of-step bin).
+void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
+    if (s->cfg.precision == TB2_F64) step_cars_t<double>(s, dt, tick, aux, stream);
+    else step_cars_t<float>(s, dt, tick, aux, stream);
+    s->launches++;
+    s->cur_pos ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
+    if (tick) { s->cur_go ^= 1; s->cur_t ^= 1; }
+    s->steps++;
 }
 
 }  // namespace
@@ -282,7 +333,8 @@ int tb2_upload(tb2_sim* s, int field, const void* src, size_t bytes, void* strea
     if (bytes && !src) return fail(TB2_ERR_INVALID, "null source");
     if (bytes) CU(cudaMemcpyAsync(s->arena + s->lay.off[b], src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     if (field == TB2_POS || field == TB2_CURSOR || field == TB2_PATH_END || field == TB2_PATH_XY ||
-        field == TB2_FACE_VEC) s->prepared = false;
+        field == TB2_FACE_VEC || field == TB2_LIGHT_XY || field == TB2_FACE_PTR || field == TB2_CELL_LIGHT_PTR ||
+        field == TB2_CELL_LIGHT_IDX) s->prepared = false;
     return TB2_OK;
 }
 
@@ -300,58 +352,29 @@ int tb2_download(const tb2_sim* s, int field, void* dst, size_t bytes, void* str
     return TB2_OK;
 }
 
-int tb2_prepare(tb2_sim* s, void* stream) {
+int tb2_prepare(tb2_sim* s, void* stream_) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
-    StepArgs64 a{};
-    fill_args(s, &a);
-    CU(cudaMemsetAsync(s->buf<char>(B_DONE), 0, s->lay.bytes[B_DONE], (cudaStream_t)stream));
-    CU(cudaMemsetAsync(s->buf<char>(B_TRIP_TIME), 0, s->lay.bytes[B_TRIP_TIME], (cudaStream_t)stream));
-    CU(cudaMemsetAsync(s->buf<char>(B_TRIP_STEP), 0, s->lay.bytes[B_TRIP_STEP], (cudaStream_t)stream));
-    launch_prepare_f64(a, s->buf<double2>(B_PT_CURV), s->buf<double2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
-                       s->cur_tab, (cudaStream_t)stream);
-    s->launches += 1 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CU(cudaMemsetAsync(s->buf<char>(B_DONE), 0, s->lay.bytes[B_DONE], stream));
+    CU(cudaMemsetAsync(s->buf<char>(B_TRIP_TIME), 0, s->lay.bytes[B_TRIP_TIME], stream));
+    CU(cudaMemsetAsync(s->buf<char>(B_TRIP_STEP), 0, s->lay.bytes[B_TRIP_STEP], stream));
     s->steps = 0;
+    if (s->cfg.precision == TB2_F64) {
+        StepArgs64 a{};
+        fill_args<double>(s, &a);
+        launch_prepare(a, s->buf<double2>(B_PT_CURV), s->buf<double2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
+                       s->cur_tab, stream);
+    } else {
+        StepArgs32 a{};
+        fill_args<float>(s, &a);
+        launch_prepare(a, s->buf<float2>(B_PT_CURV), s->buf<float2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
+                       s->cur_tab, stream);
+    }
+    s->launches += 2 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0);
     CU(cudaGetLastError());
     s->prepared = true;
     return TB2_OK;
 }
-
-}  // extern "C"
-
-namespace {
-
-// TrafficLights.update (cars.py:123-133) as its own launch
-void tick_lights(tb2_sim* s, double dt, cudaStream_t stream) {
-    StepArgs64 a{};
-    fill_args(s, &a);
-    a.dt = dt;
-    launch_lights_tick(a, stream);
-    s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
-}
-
-// Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
-// aux: also write the columns nobody can observe between steps (velocity, distances, leader, start-of-step bin).
-void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
-    const size_t C2 = (size_t)2 * s->n_cells * s->cfg.n_replicas;
-    StepArgs64 a{};
-    fill_args(s, &a);
-    a.dt = dt;
-    a.tick = tick;
-    a.write_aux = aux;
-    int32_t* tab = s->buf<int32_t>(B_TAB);
-    a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
-    a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
-    a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
-    launch_step_f64(a, stream);
-    s->launches++;
-    s->cur_pos ^= 1; s->cur_tab = (s->cur_tab + 1) % 3;
-    if (tick) { s->cur_go ^= 1; s->cur_t ^= 1; }
-    s->steps++;
-}
-
-}  // namespace
-
-extern "C" {
 
 int tb2_lights_update(tb2_sim* s, double dt, void* stream) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
@@ -362,7 +385,7 @@ int tb2_lights_update(tb2_sim* s, double dt, void* stream) {
 
 int tb2_cars_update(tb2_sim* s, double dt, void* stream) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
-    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_cars_update before tb2_prepare (positions were uploaded since)");
+    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_cars_update before tb2_prepare (state was uploaded since)");
     step_cars(s, dt, 0, s->cfg.write_aux, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return TB2_OK;
@@ -372,7 +395,7 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
     if (n_steps < 0) return fail(TB2_ERR_INVALID, "negative n_steps");
     if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
-    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (positions were uploaded since)");
+    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (state was uploaded since)");
     cudaStream_t stream = (cudaStream_t)stream_;
     for (int32_t k = 0; k < n_steps; ++k) {
         // lights-first order: L (C L) (C L) ... C - the first tick is its own launch, the rest ride in the step kernel
@@ -390,7 +413,7 @@ int tb2_step_host(tb2_sim* s, double dt, int32_t n_steps, int32_t order, const u
     const size_t F = (size_t)s->cfg.n_faces * s->cfg.n_replicas, N = (size_t)s->cfg.n_cars * s->cfg.n_replicas;
     if (face_go_in) if (int rc = tb2_upload(s, TB2_FACE_GO, face_go_in, F, stream)) return rc;
     if (int rc = tb2_step(s, dt, n_steps, order, stream)) return rc;
-    if (frame_xy_out) if (int rc = tb2_download(s, TB2_POS, frame_xy_out, N * 2 * sizeof(double), stream)) return rc;
+    if (frame_xy_out) if (int rc = tb2_download(s, TB2_POS, frame_xy_out, N * 2 * s->real_bytes(), stream)) return rc;
     if (face_go_out) if (int rc = tb2_download(s, TB2_FACE_GO, face_go_out, F, stream)) return rc;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return TB2_OK;

@@ -1,0 +1,107 @@
+// Argument block of the fused step kernel (see step_kernel.cuh), templated on the arithmetic type:
+//   double = parity mode (reference arithmetic, absolute coordinates)
+//   float  = throughput mode (coordinates relative to (origin_x, origin_y); the reference's relative tolerances are
+//            still taken from the absolute coordinate)
+// Device pointers only.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include <type_traits>
+
+#define TB2_EMPTY 0x7fffffff  // "no car" in the cell table
+
+template <typename R> struct real2;
+template <> struct real2<double> { using type = double2; };
+template <> struct real2<float> { using type = float2; };
+
+template <typename R>
+struct GridArgsT {
+    int32_t nbx, nby, ncx, n_cells;
+    R ex0, ex1, exd, ey0, ey1, eyd;  // bin edges: e[k] = k==0 ? e0 : k==1 ? e1 : e0 + k*ed   (models.py:16)
+    R inv_exd, inv_eyd;              // 1/ed, only used for the index estimate
+};
+
+// Per-cell light record, fetched in the same dependent-load wave as the cell's car-table entry: the CSR range of the
+// cell's lights plus the first light inline (position, id, face range), so the common "0 or 1 light in my bin" case
+// needs no further pointer chasing before the linspace test.  Built once by the prepare kernel.
+template <typename R>
+struct alignas(32) CellLightsT {   // exactly one 32-byte sector
+    int32_t lb;          // first entry of the cell in cell_light_idx
+    int32_t counts;      // (number of lights in the cell) | (number of faces of the first light) << 16
+    int32_t fb0, pad;    // first light: its first face
+    typename real2<R>::type xy0;   // first light: position
+};
+
+template <typename R>
+struct StepArgsT {
+    using R2 = typename real2<R>::type;
+    GridArgsT<R> g;
+    int32_t n_cars, n_lights, car_blocks, write_aux;   // n_cars / n_lights: totals over all replicas
+    int32_t n_replicas, cars_per_replica, lights_per_replica, faces_per_replica;
+    int32_t agent_car, step_index;
+    R speed_limit, stop_distance, free_distance, default_acceleration;
+    R log_free_over_stop;  // host libm log(free/stop), simulation.py:180
+    R dt;
+    R origin_x, origin_y;  // float mode: absolute = stored + origin; 0 in double mode
+    double dt64;           // lights always tick in fp64 (cars.py:130-133 is a round-off artefact, Appendix B-6)
+    // cars
+    const R2* pos_in;
+    R2* pos_out;
+    R2* vel;          // aux
+    R* route_time;
+    int32_t* cursor;
+    const int32_t* path_end;
+    const int32_t* path_eff_end;
+    const R2* path_xy;
+    const R2* pt_curv;   // per polyline point: curvature constants of the view that starts there (see prepare)
+    const R2* dest_xy;
+    R2* head_xy;      // per car: path_xy[cursor] (kept coalesced; refreshed when the cursor moves)
+    R2* head_curv;    // per car: pt_curv[cursor]
+    R* d_node;        // aux
+    R* d_car;         // aux
+    R* d_light;       // aux
+    int32_t* cell;         // bin of the current position; updated in place by the owning thread
+    int32_t* cell_prev;    // aux: bin of the start-of-step position (the reference's xbin/ybin columns)
+    int32_t* leader;       // aux
+    // cell -> (smallest, second smallest) car index; three rotating tables
+    const int2* tab_cur;
+    int32_t* tab_next;
+    int32_t* tab_clear;
+    // lights
+    const R2* light_xy;
+    const int32_t* face_ptr;
+    const R2* face_vec;
+    const R2* face_unit;  // face_vec / |face_vec| (prepare)
+    const uint8_t* go_cur;
+    const int32_t* cell_light_ptr;
+    const int32_t* cell_light_idx;
+    CellLightsT<R>* cell_lights;   // [n_cells] derived from the CSR + light arrays at prepare time
+    // fused TrafficLights.update (cars.py:123-133), runs in the trailing blocks when tick != 0
+    int32_t tick, pad;
+    const double* switch_time;
+    uint8_t* go_next;
+    const double* t_cur;
+    double* t_next;
+    // replica-ensemble bookkeeping (environment.py:120-126, 154-173)
+    int32_t* done;
+    double* trip_time;
+    int32_t* trip_step;
+};
+
+using StepArgs64 = StepArgsT<double>;
+using StepArgs32 = StepArgsT<float>;
+
+int step_block_threads();
+void launch_step(const StepArgs64& a, cudaStream_t stream);
+void launch_step(const StepArgs32& a, cudaStream_t stream);
+// (re)derive everything the step kernel keeps cached from the uploaded state: per-point curvature constants, per-car
+// head point + constants, unit face vectors, bins, and the cell table `cur_table` of the three in tab3 (all reset).
+void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3, int cur_table,
+                    cudaStream_t stream);
+void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, int32_t* tab3, int cur_table,
+                    cudaStream_t stream);
+static_assert(sizeof(CellLightsT<double>) == 32 && sizeof(CellLightsT<float>) == 32, "CellLightsT layout");
+// TrafficLights.update alone (fp64 regardless of the car arithmetic)
+void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_per_replica, double dt,
+                        const double* switch_time, const int32_t* face_ptr, const uint8_t* go_cur, uint8_t* go_next,
+                        const double* t_cur, double* t_next, cudaStream_t stream);

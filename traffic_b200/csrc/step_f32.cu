@@ -1,0 +1,10 @@
+// fp32 ("throughput mode") instantiation of the fused step kernel: state in coordinates relative to the map origin,
+// predicates evaluated in fp32 only (see step_kernel.cuh).  FMA contraction is allowed here.
+#include "step_kernel.cuh"
+
+void launch_step(const StepArgs32& a, cudaStream_t stream) { tb2k::launch_step_t<float>(a, stream); }
+
+void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, int32_t* tab3, int cur_table,
+                    cudaStream_t stream) {
+    tb2k::launch_prepare_t<float>(a, pt_curv, face_unit, n_faces, tab3, cur_table, stream);
+}

@@ -1,0 +1,544 @@
+// Fused step kernel for sm_100a, templated on the arithmetic type: one thread per car, ONE launch per simulation step.
+//
+// What one launch does (reference lines in parentheses):
+//   * FrontView: crossed-node test against the path head, target point (navigation.py:31-42, 73-111)
+//   * distance-to-node (navigation.py:62-71)
+//   * leader lookup: first other car in my 200 m bin, accepted iff it lies on my pos->target linspace in x and
+//     in y (navigation.py:422-456) - the candidate comes from a per-cell (min, 2nd-min car index) table that the
+//     PREVIOUS launch built with two atomicMin per car from the positions it wrote
+//   * red-light scan over the static cell -> lights CSR (navigation.py:459-498, models.py:90-97)
+//   * speed factor, velocity law, stall push (simulation.py:37-74, 83-186; models.py:41-66, 174-208)
+//   * Euler step (cars.py:89-90), route-cursor advance (simulation.py:47-52)
+//   * bin of the new position (models.py:7-19) + insertion into the next step's cell table
+//   * TrafficLights.update (cars.py:123-133) in the trailing blocks of the same grid (double-buffered faces, fp64)
+//
+// R = double ("parity mode", step_f64.cu, compiled with --fmad=false): every multiply/add rounds separately, as
+// numpy's ufuncs do.  The only fused operation is the explicit fma() in dot2(), which is what OpenBLAS' ddot (reached
+// by np.dot / np.linalg.norm on 2-vectors) does on the machine that recorded the golden vectors.  '/', sqrt, fmod, floor,
+// rint are IEEE-exact on the device; log/sin/cos/acos are libdevice (<= 1-2 ulp from glibc), which is why float outputs
+// are compared with a tolerance and discrete ones exactly.  The reference's predicates (np.isclose over np.linspace,
+// np.digitize, the anti-parallel face test) are FILTERED: an fp32 evaluation with an explicit error bound decides unless
+// the instance lies inside the bound's band, in which case the exact fp64 routine runs - same results, ~1 % of the
+// lanes pay for fp64 division sequences.
+//
+// R = float ("throughput mode", step_f32.cu): the same algorithm in fp32 on coordinates relative to the map origin; the
+// predicates are evaluated in fp32 only, the reference's relative tolerances still use the absolute coordinate.
+//
+// Everything that depends only on the route cursor is cached per car and refreshed when the cursor moves: the path
+// head point (coalesced instead of a 3-point gather) and the curvature constants of the 3-point view, precomputed per
+// polyline point by the prepare kernel with the same expressions.  Columns nobody can observe between the steps of a
+// batch (velocity, the three distances, leader, start-of-step bin) are only written by AUX launches.
+#pragma once
+#include "step_args.cuh"
+
+#include <math_constants.h>
+#include <type_traits>
+
+#ifndef TB2_MIN_BLOCKS
+#define TB2_MIN_BLOCKS 8
+#endif
+#ifndef TB2_BLOCK
+#define TB2_BLOCK 128   // threads per CTA of the step kernel (cars per CTA)
+#endif
+
+namespace tb2k {
+
+template <typename R> constexpr bool is_f64 = std::is_same<R, double>::value;
+
+template <typename R> struct K;
+template <> struct K<double> {
+    static constexpr double pi = 3.141592653589793;        // math.pi
+    static constexpr double half_pi = 1.5707963267948966;  // math.pi / 2
+    static constexpr double cosT = -0.9950011283222804;    // cos((pi - 0.1) / (1 + 1e-5))
+};
+template <> struct K<float> {
+    static constexpr float pi = 3.14159265358979f;
+    static constexpr float half_pi = 1.57079632679490f;
+    static constexpr float cosT = -0.9950011283222804f;
+};
+
+__device__ __forceinline__ double rsqrt_(double v) { return rsqrt(v); }
+__device__ __forceinline__ float rsqrt_(float v) { return rsqrtf(v); }
+__device__ __forceinline__ double log_(double v) { return log(v); }
+__device__ __forceinline__ float log_(float v) { return logf(v); }
+__device__ __forceinline__ double cos_(double v) { return cos(v); }
+__device__ __forceinline__ float cos_(float v) { return cosf(v); }
+__device__ __forceinline__ double sin_(double v) { return sin(v); }
+__device__ __forceinline__ float sin_(float v) { return sinf(v); }
+__device__ __forceinline__ double acos_(double v) { return acos(v); }
+__device__ __forceinline__ float acos_(float v) { return acosf(v); }
+__device__ __forceinline__ double2 mk2(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, y); }
+
+// numpy.isclose(a, b, rtol, atol)  (numeric.py:2496-2498): asymmetric in b.  b_abs is the ABSOLUTE value of b (equal
+// to b in double mode; b + origin in float mode where coordinates are stored relative to the map origin).
+template <typename R>
+__device__ __forceinline__ bool isclose_abs(R a, R b, R b_abs, R rtol, R atol) {
+    return ((fabs(a - b) <= atol + rtol * fabs(b_abs)) && isfinite(b)) || (a == b);
+}
+template <typename R>
+__device__ __forceinline__ bool isclose_(R a, R b, R rtol, R atol) { return isclose_abs<R>(a, b, b, rtol, atol); }
+
+template <typename R>
+__device__ __forceinline__ R dot2(R ax, R ay, R bx, R by) { return fma(ay, by, ax * bx); }
+template <typename R>
+__device__ __forceinline__ R norm2(R x, R y) { return sqrt(dot2<R>(x, y, x, y)); }
+template <typename R>
+__device__ __forceinline__ R clip1(R c) { return c < R(-1) ? R(-1) : (c > R(1) ? R(1) : c); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// np.digitize(x, np.arange(lo, hi, 200)): number of edges <= x, NaN -> nb  (models.py:16-17)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double edge_(int k, double e0, double e1, double d) {
+    return k == 0 ? e0 : (k == 1 ? e1 : e0 + (double)k * d);
+}
+// exact: the multiply only seeds the search; the two loops compare against the exact edges
+__device__ __forceinline__ int digitize_exact(double x, int nb, double e0, double e1, double d, double inv_d) {
+    if (nb <= 0) return 0;
+    if (isnan(x)) return nb;
+    const double q = floor((x - e0) * inv_d);
+    int k = q < -1.0 ? -1 : (q > (double)(nb - 1) ? nb - 1 : (int)q);
+    while (k + 1 < nb && edge_(k + 1, e0, e1, d) <= x) k++;
+    while (k >= 0 && edge_(k, e0, e1, d) > x) k--;
+    return k + 1;
+}
+// Filtered predicate: an fp32 estimate of the fractional bin index decides when x is at least 0.4 m (2e-3 bins) away
+// from every edge - the estimate's error is < 1e-4 bins for maps up to ~100 km - and the exact fp64 routine runs only
+// for positions inside that band (or outside the edge range, or non-finite).
+__device__ __forceinline__ int digitize_(double x, int nb, double e0, double e1, double d, double inv_d) {
+    const float fx = __double2float_rn(x - e0) * __double2float_rn(inv_d);
+    const float k = floorf(fx);
+    const float fr = fx - k;
+    if (fr > 2.0e-3f && fr < 1.0f - 2.0e-3f && k >= 0.0f && k < (float)(nb - 1) && nb < 30000) return (int)k + 1;
+    return digitize_exact(x, nb, e0, e1, d, inv_d);
+}
+// float mode: closed form on the (uniform) local edges
+__device__ __forceinline__ int digitize_(float x, int nb, float e0, float, float, float inv_d) {
+    if (nb <= 0) return 0;
+    if (isnan(x)) return nb;
+    const float q = floorf((x - e0) * inv_d) + 1.0f;
+    return q < 0.0f ? 0 : (q > (float)nb ? nb : (int)q);
+}
+template <typename R>
+__device__ __forceinline__ int cell_of(const GridArgsT<R>& g, R x, R y) {
+    return digitize_(y, g.nby, g.ey0, g.ey1, g.eyd, g.inv_eyd) * g.ncx + digitize_(x, g.nbx, g.ex0, g.ex1, g.exd, g.inv_exd);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One axis of models.upcoming_linspace (models.py:155-171): np.linspace(start, stop, n), n = int(|stop - start|).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+struct Axis {
+    R start, stop, delta;
+    int n;
+};
+template <typename R>
+__device__ __forceinline__ Axis<R> make_axis(R start, R stop) {
+    Axis<R> a;
+    a.start = start; a.stop = stop; a.delta = stop - start;
+    const R m = fabs(a.delta);
+    a.n = (m < R(2.0e9)) ? (int)m : 0;                  // int(abs(.)); Python raises on NaN/inf, we yield 0
+    return a;
+}
+// `linspace(...).any()`  (navigation.py:437, 473): non-empty and some element non-zero (absolute coordinates)
+template <typename R>
+__device__ __forceinline__ bool axis_any(const Axis<R>& a, R origin) {
+    if (a.n <= 0) return false;
+    if (a.n == 1) return !((R(0) * a.delta + (a.start + origin)) == R(0));
+    return true;
+}
+// np.isclose(np.linspace(start, stop, n)[kmin:], v, rtol=1e-6).any()   (navigation.py:443-444, 478-479), exact:
+// numpy's samples L_k = k*step + start (L_{n-1} = stop; n == 1: [0*delta + start]; function_base.py:127-175) are
+// evaluated at the nearest index and its two neighbours - the nearest sample decides, whatever the tolerance.
+static __device__ __noinline__ bool on_axis_exact(double start, double stop, int n, int kmin, double v) {
+    const double delta = stop - start;
+    const double tol = 1.0e-8 + 1.0e-6 * fabs(v);
+    const double step = (n > 1) ? delta / (double)(n - 1) : 0.0;
+    double kf = (n > 1) ? rint((v - start) / step) : 0.0;
+    kf = fmin(fmax(kf, (double)kmin), (double)(n - 1));   // NaN -> kmin
+    const int k0 = (int)kf;
+    const bool vfin = isfinite(v);
+    bool hit = false;
+#pragma unroll 1
+    for (int k = k0 - 1; k <= k0 + 1; ++k) {
+        if (k < kmin || k > n - 1) continue;
+        const double Lk = (n == 1) ? 0.0 * delta + start : ((k == n - 1) ? stop : (double)k * step + start);
+        hit |= ((fabs(Lk - v) <= tol) && vfin) || (Lk == v);
+    }
+    return hit;
+}
+// fp32 distance from v to the nearest sample with index in [kmin, n-1]  (n >= 2)
+__device__ __forceinline__ float nearest_sample_dist(float w /* v - start */, float fd /* delta */, int n, int kmin) {
+    const float fs = __fdividef(fd, (float)(n - 1));
+    float k = rintf(__fdividef(w, fs));
+    k = fminf(fmaxf(k, (float)kmin), (float)(n - 1));
+    return fabsf(w - k * fs);
+}
+// double mode: filtered predicate - the fp32 distance (error < 2e-3 m + 4e-7 * extent for n < 1e5) decides unless it is
+// within that error of the tolerance, then the exact routine runs.
+__device__ __forceinline__ bool on_axis(const Axis<double>& a, int kmin, double v, double /*origin*/) {
+    if (a.n - kmin <= 0) return false;
+    if (a.n >= 2 && a.n < 100000) {
+        const float w = __double2float_rn(v - a.start);
+        const float fd = __double2float_rn(a.delta);
+        const float r = nearest_sample_dist(w, fd, a.n, kmin);
+        const float tf = __double2float_rn(1.0e-8 + 1.0e-6 * fabs(v));
+        const float eps = 2.0e-3f + 4.0e-7f * (fabsf(w) + fabsf(fd));
+        if (r + eps < tf) return true;
+        if (r - eps > tf) return false;
+    }
+    return on_axis_exact(a.start, a.stop, a.n, kmin, v);
+}
+// float mode: the fp32 distance decides (tolerance from the absolute coordinate)
+__device__ __forceinline__ bool on_axis(const Axis<float>& a, int kmin, float v, float origin) {
+    if (a.n - kmin <= 0) return false;
+    const float w = v - a.start;
+    const float r = (a.n >= 2) ? nearest_sample_dist(w, a.delta, a.n, kmin) : fabsf(w);
+    return r <= 1.0e-8f + 1.0e-6f * fabsf(v + origin);
+}
+
+// models.get_angles on a 3-point view  (models.py:174-208, 74-87).  The reference divides each difference vector by
+// sqrt(dot(p_i, p_{i+1})) of the ABSOLUTE position vectors (sic) before normalising it; double mode reproduces that,
+// float mode (relative coordinates) skips the scale, which cancels in unit_vector.
+template <typename R>
+__device__ __noinline__ R view_angle(typename real2<R>::type p0, typename real2<R>::type p1, typename real2<R>::type p2) {
+    R ux = p1.x - p0.x, uy = p1.y - p0.y, wx = p2.x - p1.x, wy = p2.y - p1.y;
+    if constexpr (is_f64<R>) {
+        const R s01 = sqrt(dot2<R>(p0.x, p0.y, p1.x, p1.y));
+        const R s12 = sqrt(dot2<R>(p1.x, p1.y, p2.x, p2.y));
+        ux = ux / s01; uy = uy / s01; wx = wx / s12; wy = wy / s12;
+    }
+    const R nu = norm2<R>(ux, uy), nw = norm2<R>(wx, wy);
+    const R c = clip1<R>(dot2<R>(ux / nu, uy / nu, wx / nw, wy / nw));
+    R a = acos_(c);
+    if (a > K<R>::half_pi) a = a - K<R>::half_pi;
+    return a;
+}
+
+// Curvature constants of the view whose head is polyline point q of a car whose polyline ends at `end`
+// (simulation.road_curvature_factor, simulation.py:135-164): returns (s, L) with
+//   s = stop*2*theta/pi and L = log(free/s), or s = 0 when the factor is identically 1 (theta isclose 0).
+template <typename R>
+__device__ __forceinline__ typename real2<R>::type curv_constants(const typename real2<R>::type* __restrict__ path_xy,
+                                                                  int q, int end, R stop_d, R free_d) {
+    const int len = end - q;
+    R theta;
+    if (len == 1) theta = K<R>::half_pi;
+    else if (len >= 3) theta = view_angle<R>(path_xy[q], path_xy[q + 1], path_xy[q + 2]);
+    else theta = R(0);  // models.get_angles returns False
+    if (isclose_<R>(theta, R(0), R(1.0e-1), R(1.0e-8))) return mk2(R(0), R(0));
+    const R s = stop_d * 2 * theta / K<R>::pi;
+    return mk2(s, log_(free_d / s));
+}
+
+// models.determine_anti_parallel_vectors over the red faces of light l  (navigation.py:481-489, models.py:90-97).
+// face_unit holds unit_vector(face) = face / norm(face), computed once by the prepare kernel with the reference's
+// expression.  np.isclose(pi, angle, atol=0.1) is true iff angle >= T = (pi - 0.1) / (1 + 1e-5); acos is monotone, so
+// the cosine decides: an fp32 cosine when it is further than 1e-4 from cos(T), the reference's fp64 expression
+// otherwise, and acos itself only inside a +-1e-6 band.  Float mode: the fp32 cosine decides.
+static __device__ __noinline__ bool antiparallel_exact(double cvx, double cvy, double2 fu) {
+    const double ncv = norm2<double>(cvx, cvy);
+    const double c = clip1<double>(dot2<double>(cvx / ncv, cvy / ncv, fu.x, fu.y));
+    if (c < K<double>::cosT - 1.0e-6) return true;
+    if (c > K<double>::cosT + 1.0e-6) return false;
+    return isclose_<double>(K<double>::pi, acos(c), 1.0e-5, 0.1);
+}
+template <typename R>
+__device__ __forceinline__ bool red_face_ahead(const StepArgsT<R>& a, int fb, int fe, int fbase, R cvx, R cvy) {
+    const float fx = (float)cvx, fy = (float)cvy;
+    const float inv = rsqrtf(fx * fx + fy * fy);
+    bool found = false;
+    for (int f = fb; f < fe && !found; ++f) {
+        if (a.go_cur[fbase + f]) continue;
+        const typename real2<R>::type fu = a.face_unit[f];
+        const float c = (fx * (float)fu.x + fy * (float)fu.y) * inv;
+        if constexpr (is_f64<R>) {
+            if (c < (float)K<double>::cosT - 1.0e-4f) found = true;
+            else if (!(c > (float)K<double>::cosT + 1.0e-4f)) found = antiparallel_exact(cvx, cvy, fu);
+        } else {
+            found = c <= K<float>::cosT;
+        }
+    }
+    return found;
+}
+
+// TrafficLights.update  (cars.py:130-133); lg runs over replicas x lights, geometry (face_ptr) is shared.  Always fp64.
+__device__ __forceinline__ void lights_tick_body(int lg, int n_lights_total, int lights_per_replica, int faces_per_replica,
+                                                 double dt, const double* __restrict__ switch_time,
+                                                 const int32_t* __restrict__ face_ptr, const uint8_t* __restrict__ go_cur,
+                                                 uint8_t* __restrict__ go_next, const double* t_cur, double* t_next) {
+    const double t = __dadd_rn(*t_cur, dt);
+    if (lg == 0) *t_next = t;
+    if (lg >= n_lights_total) return;
+    const int rep = lg / lights_per_replica, l = lg - rep * lights_per_replica;
+    const int fbase = rep * faces_per_replica;
+    const double sw = switch_time[lg];
+    double r = fmod(t, sw);                       // numpy float remainder
+    if (r != 0.0 && ((sw < 0.0) != (r < 0.0))) r = __dadd_rn(r, sw);
+    // isclose(0, r, rtol=1e-4): |0 - r| <= 1e-8 + 1e-4*|r|
+    const bool s = ((fabs(r) <= __dadd_rn(1.0e-8, __dmul_rn(1.0e-4, fabs(r)))) && isfinite(r)) || (r == 0.0);
+    for (int f = face_ptr[l]; f < face_ptr[l + 1]; ++f) go_next[fbase + f] = s ? (uint8_t)!go_cur[fbase + f] : go_cur[fbase + f];
+}
+
+__device__ __forceinline__ void table_insert(int32_t* tab, int cell, int i) {
+    const int old = atomicMin(&tab[2 * cell], i);
+    const int loser = old > i ? old : i;   // whoever is not the cell minimum competes for second place
+    if (loser != TB2_EMPTY) atomicMin(&tab[2 * cell + 1], loser);
+}
+
+// AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell tables / face states, agent
+// arrival bookkeeping); a single simulation compiles these out.
+template <typename R, bool AUX, bool ENS>
+__global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const __grid_constant__ StepArgsT<R> a) {
+    using R2 = typename real2<R>::type;
+    if ((int)blockIdx.x >= a.car_blocks) {
+        const int l = ((int)blockIdx.x - a.car_blocks) * TB2_BLOCK + (int)threadIdx.x;
+        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
+                         a.go_cur, a.go_next, a.t_cur, a.t_next);
+        return;
+    }
+    const int i = (int)blockIdx.x * TB2_BLOCK + (int)threadIdx.x;
+    // reset the table that the launch after next will fill
+    for (int k = i; k < 2 * a.g.n_cells * a.n_replicas; k += a.car_blocks * TB2_BLOCK) a.tab_clear[k] = TB2_EMPTY;
+    if (i >= a.n_cars) return;
+    // replica of this car (1 for a single simulation): offsets into the per-replica cell tables and face states
+    const int rep = ENS ? i / a.cars_per_replica : 0;
+    const int cbase = rep * a.g.n_cells, fbase = rep * a.faces_per_replica, ibase = rep * a.cars_per_replica;
+
+    // ---- independent loads first ----
+    const R2 p = a.pos_in[i];
+    const int cur = a.cursor[i];
+    const int end = a.path_end[i];
+    const int eff = a.path_eff_end[i];
+    const int c = a.cell[i];
+    const R2 head = a.head_xy[i];
+    const R2 hc = a.head_curv[i];
+    const R rt = a.route_time[i];
+    // ---- dependent on the bin ----
+    const int2 m = a.tab_cur[cbase + c];
+    const CellLightsT<R> cl = a.cell_lights[c];
+    const int lb = cl.lb, le = cl.lb + (cl.counts & 0xffff);
+
+    const R x = p.x, y = p.y;
+    const bool has_path = cur < eff;
+    const int path_len = has_path ? end - cur : 0;
+    // FrontView.crossed_node_event (navigation.py:91-111): tolerance relative to the car's ABSOLUTE coordinate
+    const bool crossed = has_path && isclose_abs<R>(head.x, x, x + a.origin_x, R(1.0e-5), R(1.0e-8)) &&
+                         isclose_abs<R>(head.y, y, y + a.origin_y, R(1.0e-5), R(1.0e-8));
+    R2 t = head;
+    if (!has_path || (crossed && path_len < 2)) t = a.dest_xy[i];
+    else if (crossed) t = a.path_xy[cur + 1];
+
+    const R dx = t.x - x, dy = t.y - y;
+    const R d_node = norm2<R>(dx, dy);
+    const Axis<R> ax = make_axis<R>(x, t.x), ay = make_axis<R>(y, t.y);
+    const bool spaces = axis_any<R>(ax, a.origin_x) && axis_any<R>(ay, a.origin_y);
+
+    // ---- leader lookup (navigation.car_obstacles) ----
+    R d_car = R(0);
+    int lead = -1;
+    const int j = (m.x != i) ? m.x : m.y;
+    if (spaces && j != TB2_EMPTY) {
+        const R2 o = a.pos_in[j];
+        if (on_axis(ax, 0, o.x, a.origin_x) && on_axis(ay, 0, o.y, a.origin_y)) {
+            d_car = norm2<R>(o.x - x, o.y - y);
+            if (d_car != R(0)) lead = j;
+        }
+    }
+    // ---- red-light scan (navigation.light_obstacles) ----
+    R d_light = R(0);
+    if (spaces && lb < le) {
+        d_light = -R(0);  // loop exhausted -> None
+        for (int q = lb; q < le; ++q) {
+            // the first light of the bin came with the cell record; further ones (rare) go through the CSR
+            const int l = (q == lb) ? -1 : a.cell_light_idx[q];
+            const R2 lp = (q == lb) ? cl.xy0 : a.light_xy[l];
+            if (on_axis(ax, 1, lp.x, a.origin_x) && on_axis(ay, 1, lp.y, a.origin_y)) {
+                const R cvx = lp.x - x, cvy = lp.y - y;
+                const int fb = (q == lb) ? cl.fb0 : a.face_ptr[l];
+                const int fe = (q == lb) ? cl.fb0 + (cl.counts >> 16) : a.face_ptr[l + 1];
+                if (red_face_ahead<R>(a, fb, fe, fbase, cvx, cvy)) { d_light = norm2<R>(cvx, cvy); break; }
+            } else { d_light = R(0); break; }
+        }
+    }
+
+    // ---- velocity law + route advance (simulation.update_cars) ----
+    R vx = R(0), vy = R(0);
+    if (has_path) {
+        a.route_time[i] = rt + a.dt;
+        // Both speed factors have the form log(d / den) / L on (stop, free]:
+        //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den) (cached)
+        //   simulation.obstacle_factor       (simulation.py:167-186): den = stop,            L = log(free/stop)
+        // so they share one code path.  Pass 0 evaluates the factor the car actually uses (obstacle factor when it
+        // has an obstacle, curvature factor otherwise); pass 1 only runs for cars that blend both (models.weigh_factors).
+        const bool c_t = d_car != R(0), r_t = d_light != R(0);  // Python truthiness (NaN truthy)
+        const bool obs = c_t || r_t;
+        const bool weigh = c_t && !r_t && d_car > d_node;      // simulation.py:120-126
+        const R d_obs = (c_t && r_t) ? ((d_car <= d_light) ? d_car : d_light) : (c_t ? d_car : d_light);
+        R r0 = R(1), r1 = R(1);
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+            const bool as_obs = (it == 0) && obs;
+            const bool wanted = (it == 0) ? (obs || hc.x != R(0)) : (weigh && hc.x != R(0));
+            const R d = as_obs ? d_obs : d_node;
+            const R den = as_obs ? a.stop_distance : hc.x;
+            const R L = as_obs ? a.log_free_over_stop : hc.y;
+            R r = R(1);
+            if (wanted) {
+                if (a.stop_distance < d && d <= a.free_distance) r = log_(d / den) / L;
+                else if (as_obs && d <= a.stop_distance) r = R(0);
+            }
+            if (it == 0) r0 = r; else r1 = r;
+        }
+        R f = r0;   // curvature factor without an obstacle, obstacle factor with one
+        if (weigh) f = r0 * cos_(d_car / a.free_distance) + r1 * sin_(d_node / a.free_distance);  // models.py:41-66
+        f = fabs(f);
+        vx = dx / d_node * a.speed_limit * f;
+        vy = dy / d_node * a.speed_limit * f;
+        if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) && isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
+            const bool acc = !r_t && (!c_t || d_car > a.stop_distance);
+            if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
+        }
+        if (crossed) {
+            a.cursor[i] = cur + 1;
+            if (cur + 1 < end) {          // new head: the point we just steered to
+                a.head_xy[i] = t;
+                a.head_curv[i] = a.pt_curv[cur + 1];
+            }
+        }
+    } else if (cur != end) {
+        a.cursor[i] = end;  // path becomes []
+    }
+    const R xn = x + vx * a.dt, yn = y + vy * a.dt;  // cars.py:89-90
+    a.pos_out[i] = mk2(xn, yn);
+    if (AUX) {
+        a.vel[i] = mk2(vx, vy);
+        a.d_node[i] = d_node;
+        a.d_car[i] = d_car;
+        a.d_light[i] = d_light;
+        a.leader[i] = lead >= 0 ? lead - ibase : -1;
+        a.cell_prev[i] = c;
+    }
+    // ---- bin of the new position + insertion into the next step's table ----
+    const int cn = cell_of<R>(a.g, xn, yn);
+    if (cn != c) a.cell[i] = cn;
+    table_insert(a.tab_next, cbase + cn, i);
+    // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
+    // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
+    if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
+        const R2 d = a.dest_xy[i];
+        if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
+            a.done[rep] = 1;
+            a.trip_time[rep] = (double)rt;
+            a.trip_step[rep] = a.step_index;
+        }
+    }
+}
+
+// prepare, pass 1: curvature constants of every polyline point still ahead of its car
+template <typename R>
+__global__ void __launch_bounds__(128) prepare_points_kernel(int n_cars, const int32_t* __restrict__ cursor,
+                                                             const int32_t* __restrict__ path_end,
+                                                             const typename real2<R>::type* __restrict__ path_xy,
+                                                             typename real2<R>::type* pt_curv, R stop_d, R free_d) {
+    const int i = (int)blockIdx.x * 128 + (int)threadIdx.x;
+    if (i >= n_cars) return;
+    const int end = path_end[i];
+    for (int q = cursor[i]; q < end; ++q) pt_curv[q] = curv_constants<R>(path_xy, q, end, stop_d, free_d);
+}
+
+// prepare, pass 2: per-car head cache, bin, cell-table insertion
+template <typename R>
+__global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgsT<R> g,
+                                                           const typename real2<R>::type* __restrict__ pos,
+                                                           const int32_t* __restrict__ cursor,
+                                                           const int32_t* __restrict__ path_end,
+                                                           const typename real2<R>::type* __restrict__ path_xy,
+                                                           const typename real2<R>::type* __restrict__ pt_curv,
+                                                           typename real2<R>::type* head_xy,
+                                                           typename real2<R>::type* head_curv, int32_t* cell,
+                                                           int32_t* cell_prev, int32_t* tab, int cars_per_replica) {
+    const int i = (int)blockIdx.x * 256 + (int)threadIdx.x;
+    if (i >= n_cars) return;
+    const int cur = cursor[i];
+    typename real2<R>::type h = mk2(R(0), R(0)), hc = h;
+    if (cur < path_end[i]) { h = path_xy[cur]; hc = pt_curv[cur]; }
+    head_xy[i] = h;
+    head_curv[i] = hc;
+    const typename real2<R>::type p = pos[i];
+    const int cn = cell_of<R>(g, p.x, p.y);
+    cell[i] = cn;
+    cell_prev[i] = cn;
+    table_insert(tab, (i / cars_per_replica) * g.n_cells + cn, i);
+}
+
+// prepare: unit vectors of the light faces (models.unit_vector, models.py:74-76)
+template <typename R>
+__global__ void __launch_bounds__(256) prepare_faces_kernel(int n_faces, const typename real2<R>::type* __restrict__ face_vec,
+                                                            typename real2<R>::type* __restrict__ face_unit) {
+    const int f = (int)blockIdx.x * 256 + (int)threadIdx.x;
+    if (f >= n_faces) return;
+    const typename real2<R>::type fv = face_vec[f];
+    const R nf = norm2<R>(fv.x, fv.y);
+    face_unit[f] = mk2(fv.x / nf, fv.y / nf);
+}
+
+// prepare: per-cell light records (CSR range + first light inline)
+template <typename R>
+__global__ void __launch_bounds__(256) prepare_cells_kernel(int n_cells, const int32_t* __restrict__ cell_light_ptr,
+                                                            const int32_t* __restrict__ cell_light_idx,
+                                                            const typename real2<R>::type* __restrict__ light_xy,
+                                                            const int32_t* __restrict__ face_ptr, CellLightsT<R>* out) {
+    const int c = (int)blockIdx.x * 256 + (int)threadIdx.x;
+    if (c >= n_cells) return;
+    CellLightsT<R> r{};
+    const int lb = cell_light_ptr[c], le = cell_light_ptr[c + 1];
+    int nl = le - lb, nf0 = 0;
+    r.lb = lb; r.fb0 = 0; r.xy0 = mk2(R(0), R(0));
+    if (nl > 0) {
+        const int l = cell_light_idx[lb];
+        r.xy0 = light_xy[l]; r.fb0 = face_ptr[l]; nf0 = face_ptr[l + 1] - face_ptr[l];
+    }
+    r.counts = (nl & 0xffff) | (nf0 << 16);   // config_ok() bounds both below 2^15
+    out[c] = r;
+}
+
+static __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
+}
+
+template <typename R>
+void launch_step_t(const StepArgsT<R>& a, cudaStream_t stream) {
+    const int lb = (a.n_lights + TB2_BLOCK - 1) / TB2_BLOCK;
+    const int light_blocks = a.tick ? (lb > 0 ? lb : 1) : 0;
+    const int grid = a.car_blocks + light_blocks;
+    if (grid <= 0) return;
+    const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
+    if (ens) {
+        if (a.write_aux) step_kernel<R, true, true><<<grid, TB2_BLOCK, 0, stream>>>(a);
+        else step_kernel<R, false, true><<<grid, TB2_BLOCK, 0, stream>>>(a);
+    } else {
+        if (a.write_aux) step_kernel<R, true, false><<<grid, TB2_BLOCK, 0, stream>>>(a);
+        else step_kernel<R, false, false><<<grid, TB2_BLOCK, 0, stream>>>(a);
+    }
+}
+
+template <typename R>
+void launch_prepare_t(const StepArgsT<R>& a, typename real2<R>::type* pt_curv, typename real2<R>::type* face_unit,
+                      int n_faces, int32_t* tab3, int cur_table, cudaStream_t stream) {
+    const size_t n = (size_t)6 * a.g.n_cells * a.n_replicas;
+    const size_t blocks = (n + 255) / 256;
+    fill_i32_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(tab3, n, TB2_EMPTY);
+    if (n_faces > 0) prepare_faces_kernel<R><<<(n_faces + 255) / 256, 256, 0, stream>>>(n_faces, a.face_vec, face_unit);
+    prepare_cells_kernel<R><<<(a.g.n_cells + 255) / 256, 256, 0, stream>>>(a.g.n_cells, a.cell_light_ptr, a.cell_light_idx,
+                                                                          a.light_xy, a.face_ptr, a.cell_lights);
+    if (a.n_cars > 0) {
+        prepare_points_kernel<R><<<(a.n_cars + 127) / 128, 128, 0, stream>>>(a.n_cars, a.cursor, a.path_end, a.path_xy,
+                                                                               pt_curv, a.stop_distance, a.free_distance);
+        prepare_cars_kernel<R><<<(a.n_cars + 255) / 256, 256, 0, stream>>>(
+            a.n_cars, a.g, a.pos_in, a.cursor, a.path_end, a.path_xy, pt_curv, a.head_xy, a.head_curv, a.cell,
+            a.cell_prev, tab3 + (size_t)2 * a.g.n_cells * a.n_replicas * cur_table, a.cars_per_replica);
+    }
+}
+
+}  // namespace tb2k

@@ -55,7 +55,7 @@ class Ensemble:
     """R replicas of ``world`` on one GPU.  ``replica_ids`` are the global ids of the replicas this rank owns."""
 
     def __init__(self, world: World, replica_ids, agent_car: int, seed: int = 0, switch_time=None, device=None,
-                 write_aux: bool = False):
+                 write_aux: bool = False, precision: int = native.F64):
         self.world = world
         self.replica_ids = np.asarray(replica_ids, np.int64)
         R = len(self.replica_ids)
@@ -65,8 +65,8 @@ class Ensemble:
             all_sw = random_switch_times(world, int(self.replica_ids.max()) + 1, seed)
             switch_time = all_sw[self.replica_ids]
         self.switch_time = np.ascontiguousarray(switch_time, np.float64).reshape(R, world.n_lights)
-        self.sim = native.DeviceSim(world, write_aux=write_aux, device=device, n_replicas=R, agent_car=agent_car,
-                                    switch_time=self.switch_time)
+        self.sim = native.DeviceSim(world, precision=precision, write_aux=write_aux, device=device, n_replicas=R,
+                                    agent_car=agent_car, switch_time=self.switch_time)
         self.agent_car = agent_car
 
     def rollout(self, dt: float, max_steps: int, chunk: int = 500, order: int = native.ORDER_LIGHTS_CARS):

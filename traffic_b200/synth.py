@@ -210,7 +210,7 @@ def make_lights(graph: SynthGraph, prescale: int = 10, seed: int = 0):
 
 def make_city(nx_: int, ny_: int, n_cars: int, prescale: int = 10, seed: int = 0, x0: float = 551000.0,
               y0: float = 4180000.0, max_hops: int = 40, max_points: int = 64, n_sources: int = 256,
-              stagger: bool = True):
+              stagger: bool = True, spatial_order: bool = False):
     """A full synthetic ``World`` (graph + routed cars + lights) of arbitrary size, same semantics as a world packed
     from the reference's DataFrames.  With ``stagger`` each car starts at a random point of its first edge and its
     polyline starts at that edge's far end, so co-located starts with identical routes (mutually invisible forever,
@@ -235,7 +235,17 @@ def make_city(nx_: int, ny_: int, n_cars: int, prescale: int = 10, seed: int = 0
     else:
         pos = path_xy[start].copy()
     lights = make_lights(g, prescale=prescale, seed=seed + 3)
-    w = make_world(g.axis, pos, path_ptr, path_xy, g.node_xy[dest], lights)
+    dest_xy = g.node_xy[dest]
+    if spatial_order:  # experiment knob: number the cars in bin order of their start positions
+        from .state import Grid, digitize_cells
+        order = np.argsort(digitize_cells(Grid.from_axis(g.axis), pos), kind="stable")
+        lens = np.diff(path_ptr)[order]
+        starts = path_ptr[:-1][order]
+        idx = np.concatenate([np.arange(a, a + n) for a, n in zip(starts, lens)]) if len(order) else np.zeros(0, np.int64)
+        path_xy = path_xy[idx]
+        path_ptr = np.concatenate([[0], np.cumsum(lens)])
+        pos, dest_xy = pos[order], dest_xy[order]
+    w = make_world(g.axis, pos, path_ptr, path_xy, dest_xy, lights)
     return w, g
 
 
