@@ -184,6 +184,9 @@ def main():
                     help="c4_city_1m | c3_sf_50k | c2_manhattan_2k (one simulation per GPU) | c5_ensemble (--replicas "
                          "rollouts of the 2k-car world, sharded over the GPUs)")
     ap.add_argument("--replicas", type=int, default=4096, help="c5_ensemble: total number of replicas")
+    ap.add_argument("--neighbor", default="atomic", choices=["atomic", "sort"],
+                    help="how the per-bin leader table is built: atomicMin at the kernel tail (default) or the radix-sort "
+                         "pipeline (same results)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
                     help="f64: parity mode (reference arithmetic, bit-exact discrete outputs); f32: throughput mode")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
@@ -231,7 +234,8 @@ def main():
         N = w.n_cars * len(ids)
     else:
         w = make_workload(args.workload, args.seed + rank)  # every rank: an independent replica (different seed)
-        sim = native.DeviceSim(w, precision=prec, write_aux=True)
+        sim = native.DeviceSim(w, precision=prec, write_aux=True,
+                               neighbor_mode=native.NEIGHBOR_SORT if args.neighbor == "sort" else native.NEIGHBOR_ATOMIC)
         N = w.n_cars
 
     # ---- device-resident throughput ----
@@ -303,7 +307,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        kernel_us = ms / launches * 1e3 if launches else float("nan")
+        # mean duration of the step kernel; with --neighbor sort the sort launches share the step, so this is an upper bound
+        kernel_us = ms / args.steps * 1e3
         algo = ALGO_BYTES[args.precision] * N
         achieved = algo / (kernel_us * 1e-6) / 1e9
         traffic = None
@@ -323,6 +328,7 @@ def main():
                        "lights": w.n_lights, "faces": w.n_faces,
                        "path_points": int(len(w.path_xy)), "cells": w.grid.n_cells, "dt": dt,
                        "order": "cars_then_lights", "replicas": world, "parallelism": "replica-per-gpu",
+                       "neighbor": args.neighbor,
                        "l2": "working set %.0f MB per step > %.0f MB L2, no explicit flush" % (ws / 1e6, L2_BYTES / 1e6),
                        "frame_every_k_steps": k},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -32,6 +32,10 @@ extern "C" {
 #define TB2_ORDER_CARS_LIGHTS 0 /* test/profile_cars_update.py:29-34 */
 #define TB2_ORDER_LIGHTS_CARS 1 /* animate.py:63-64, environment.py:167-168 */
 
+/* how the per-bin (first, second) car-index table behind the leader lookup is built each step */
+#define TB2_NEIGHBOR_ATOMIC 0 /* two atomicMin per car at the tail of the step kernel (default, no extra launch)      */
+#define TB2_NEIGHBOR_SORT 1   /* stable radix sort of the cars by bin + warp-shuffle segment heads (same result)       */
+
 /* arithmetic modes */
 #define TB2_F64 0 /* reference arithmetic (numpy float64 evaluation order) - parity mode            */
 #define TB2_F32 1 /* throughput mode: fp32 state in local-origin coordinates, tolerances from absolute */
@@ -92,7 +96,7 @@ typedef struct tb2_config {
     int32_t write_aux;   /* 1: TB2_VEL, TB2_D_*, TB2_LEADER and TB2_CELL are valid after every tb2_cars_update and
                           *    after the LAST step of every tb2_step batch (columns nobody can observe between the steps
                           *    of a batch are not written); 0: never written (pure stepping) */
-    int32_t reserved;
+    int32_t neighbor_mode; /* TB2_NEIGHBOR_ATOMIC (default) | TB2_NEIGHBOR_SORT */
     /* Replica ensemble: n_replicas independent copies of the same world (same graph, routes and light geometry) with
      * their own car state, light timings (TB2_SWITCH_TIME [R*L]) and face states (TB2_FACE_GO [R*F]), advanced by
      * the same launches.  n_cars / n_lights / n_faces are PER REPLICA; per-car fields hold R*n_cars elements, replica

@@ -221,3 +221,34 @@ def test_f32_throughput_mode_tracks_f64():
     assert (a.cursor == b.cursor).mean() >= 0.998
     assert (rel <= 1e-5).mean() >= 0.998
     assert np.array_equal(a.face_go, b.face_go) and abs(a.lights_time - b.lights_time) == 0.0
+
+
+@pytest.mark.parametrize("replicas", [1, 3])
+def test_sort_neighbour_source_equals_atomic_table(replicas):
+    """north_star's neighbour pipeline (stable radix sort of the cars by bin + warp-shuffle segment heads) and the default
+    atomicMin table must give bit-identical simulations, and both must match the golden record."""
+    native = _native()
+    from traffic_b200 import synth
+
+    w0, _ = synth.make_city(nx_=40, ny_=40, n_cars=20000, prescale=3, seed=41)
+    outs = []
+    for mode in (native.NEIGHBOR_ATOMIC, native.NEIGHBOR_SORT):
+        w = w0.copy()
+        sim = native.DeviceSim(w, neighbor_mode=mode, n_replicas=replicas)
+        sim.step(1e-3, 150, 1)
+        outs.append(sim.download_world(w, replica=replicas - 1))
+    a, b = outs
+    for f in ("pos", "vel", "route_time", "cursor", "d_node", "d_car", "d_light", "cell", "leader", "face_go"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+    assert (a.leader >= 0).sum() > 100
+    if replicas == 1:
+        g = util.load_golden("dense_dt0.001_p2_s3")
+        w = util.world_from_golden(g)
+        start = w.path_start.copy()
+        sim = native.DeviceSim(w, neighbor_mode=native.NEIGHBOR_SORT)
+        report = []
+        for t in range(120):
+            sim.step(float(g["dt"]), 1, util.order_code(g))
+            sim.download_world(w)
+            ok, _ = util.compare_step(util.snapshot(w, start), g, t, w.grid.ncx, FLOAT_RTOL, report)
+            assert ok, "\\n".join(report[:5])

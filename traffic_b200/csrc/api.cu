@@ -40,7 +40,8 @@ enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
     B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
     B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV,
-    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_LIGHTS, B_COUNT
+    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_LIGHTS, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
+    B_SORT_VALS_OUT, B_SORT_TEMP, B_COUNT
 };
 
 struct Layout {
@@ -63,7 +64,15 @@ bool config_ok(const tb2_config* c, std::string* why) {
     if ((int64_t)c->n_replicas * c->n_cars >= ((int64_t)1 << 31) - 1) { *why = "more than 2^31 cars"; return false; }
     if ((int64_t)c->n_replicas * (c->nbx + 1) * (c->nby + 1) > (int64_t)1 << 29) { *why = "too many cells x replicas"; return false; }
     if (c->agent_car >= c->n_cars) { *why = "agent_car out of range"; return false; }
+    if (c->neighbor_mode != TB2_NEIGHBOR_ATOMIC && c->neighbor_mode != TB2_NEIGHBOR_SORT) { *why = "bad neighbor_mode"; return false; }
     return true;
+}
+
+int key_bits_of(const tb2_config& c) {
+    const int64_t n_keys = (int64_t)c.n_replicas * (c.nbx + 1) * (c.nby + 1);
+    int bits = 1;
+    while (((int64_t)1 << bits) < n_keys) ++bits;
+    return bits;
 }
 
 Layout make_layout(const tb2_config& c) {
@@ -98,6 +107,9 @@ Layout make_layout(const tb2_config& c) {
     b[B_DONE] = b[B_TRIP_STEP] = Rep * 4;
     b[B_TRIP_TIME] = Rep * 8;
     b[B_CELL_LIGHTS] = C * 32;
+    const bool sorted = c.neighbor_mode == TB2_NEIGHBOR_SORT;
+    b[B_SORT_KEYS_IN] = b[B_SORT_VALS_IN] = b[B_SORT_KEYS_OUT] = b[B_SORT_VALS_OUT] = sorted ? N * 4 : 0;
+    b[B_SORT_TEMP] = sorted ? neighbor_sort_temp_bytes((int)N, key_bits_of(c)) : 0;
     size_t off = 0;
     for (int i = 0; i < B_COUNT; ++i) {
         l.off[i] = off;
@@ -241,7 +253,13 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
     a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
     a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
     a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
+    a.skip_insert = s->cfg.neighbor_mode == TB2_NEIGHBOR_SORT;
     launch_step(a, stream);
+    if (a.skip_insert)   // north_star's pipeline: radix sort by bin + segment heads -> the same table
+        s->launches += neighbor_sort_build(a.n_cars, a.cars_per_replica, s->n_cells, key_bits_of(s->cfg), a.cell,
+                                           s->buf<int32_t>(B_SORT_KEYS_IN), s->buf<int32_t>(B_SORT_VALS_IN),
+                                           s->buf<int32_t>(B_SORT_KEYS_OUT), s->buf<int32_t>(B_SORT_VALS_OUT),
+                                           s->buf<char>(B_SORT_TEMP), s->lay.bytes[B_SORT_TEMP], a.tab_next, stream);
 }
 
 // Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.

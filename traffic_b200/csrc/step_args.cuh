@@ -39,6 +39,7 @@ struct StepArgsT {
     int32_t n_cars, n_lights, car_blocks, write_aux;   // n_cars / n_lights: totals over all replicas
     int32_t n_replicas, cars_per_replica, lights_per_replica, faces_per_replica;
     int32_t agent_car, step_index;
+    int32_t skip_insert, pad0;   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
     R speed_limit, stop_distance, free_distance, default_acceleration;
     R log_free_over_stop;  // host libm log(free/stop), simulation.py:180
     R dt;
@@ -101,6 +102,11 @@ void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, i
 void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, int32_t* tab3, int cur_table,
                     cudaStream_t stream);
 static_assert(sizeof(CellLightsT<double>) == 32 && sizeof(CellLightsT<float>) == 32, "CellLightsT layout");
+// sort-based neighbour source (neighbor_sort.cu)
+size_t neighbor_sort_temp_bytes(int n_cars, int key_bits);
+int neighbor_sort_build(int n_cars, int cars_per_replica, int n_cells, int key_bits, const int32_t* cell, int32_t* keys_in,
+                        int32_t* vals_in, int32_t* keys_out, int32_t* vals_out, void* temp, size_t temp_bytes,
+                        int32_t* tab, cudaStream_t stream);
 // TrafficLights.update alone (fp64 regardless of the car arithmetic)
 void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_per_replica, double dt,
                         const double* switch_time, const int32_t* face_ptr, const uint8_t* go_cur, uint8_t* go_next,

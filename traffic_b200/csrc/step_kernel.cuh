@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
     if (cn != c) a.cell[i] = cn;
-    table_insert(a.tab_next, cbase + cn, i);
+    if (!a.skip_insert) table_insert(a.tab_next, cbase + cn, i);
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {

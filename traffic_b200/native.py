@@ -23,6 +23,7 @@ ABI_VERSION = 2
 ORDER_CARS_LIGHTS = 0  # test/profile_cars_update.py:29-34
 ORDER_LIGHTS_CARS = 1  # animate.py:63-64, environment.py:167-168
 F64, F32 = 0, 1
+NEIGHBOR_ATOMIC, NEIGHBOR_SORT = 0, 1
 
 # tb2_field
 (POS, VEL, ROUTE_TIME, CURSOR, PATH_END, PATH_EFF_END, PATH_XY, DEST_XY, D_NODE, D_CAR, D_LIGHT, CELL, LEADER,
@@ -45,7 +46,7 @@ class Tb2Config(C.Structure):
                 ("speed_limit", C.c_double), ("stop_distance", C.c_double), ("free_distance", C.c_double),
                 ("default_acceleration", C.c_double),
                 ("origin_x", C.c_double), ("origin_y", C.c_double),
-                ("write_aux", C.c_int32), ("reserved", C.c_int32),
+                ("write_aux", C.c_int32), ("neighbor_mode", C.c_int32),
                 ("n_replicas", C.c_int32), ("agent_car", C.c_int32)]
 
 
@@ -105,13 +106,14 @@ def _check(rc: int, what: str):
         raise NativeError("%s failed (status %d): %s" % (what, rc, lib().tb2_last_error().decode()))
 
 
-def config_of(w: World, precision: int = F64, write_aux: bool = True, n_replicas: int = 1, agent_car: int = -1) -> Tb2Config:
+def config_of(w: World, precision: int = F64, write_aux: bool = True, n_replicas: int = 1, agent_car: int = -1,
+              neighbor_mode: int = 0) -> Tb2Config:
     """``w`` describes ONE replica; per-car arrays of an ensemble are tiled by the caller (``traffic_b200.ensemble``)."""
     g, p = w.grid, w.params
     return Tb2Config(ABI_VERSION, precision, w.n_cars, w.n_lights, w.n_faces, len(w.cell_light_idx), len(w.path_xy),
                      g.nbx, g.nby, g.ex[0], g.ex[1], g.ex[2], g.ey[0], g.ey[1], g.ey[2],
                      p["speed_limit"], p["stop_distance"], p["free_distance"], p["default_acceleration"],
-                     g.axis[0], g.axis[2], 1 if write_aux else 0, 0, n_replicas, agent_car)
+                     g.axis[0], g.axis[2], 1 if write_aux else 0, neighbor_mode, n_replicas, agent_car)
 
 
 _NP_OF_FIELD = {POS: np.float64, VEL: np.float64, ROUTE_TIME: np.float64, CURSOR: np.int32, PATH_END: np.int32,
@@ -127,7 +129,8 @@ class DeviceSim:
     """One simulation resident on one GPU.  ``step`` is asynchronous on the current torch stream."""
 
     def __init__(self, world: World, precision: int = F64, write_aux: bool = True, device=None,
-                 n_replicas: int = 1, agent_car: int = -1, switch_time=None, face_go=None):
+                 n_replicas: int = 1, agent_car: int = -1, switch_time=None, face_go=None,
+                 neighbor_mode: int = NEIGHBOR_ATOMIC):
         """``world`` describes one replica.  With ``n_replicas`` > 1 the car state is tiled and ``switch_time``
         ``[R, L]`` / ``face_go`` ``[R, F]`` may give every replica its own light timings (default: the world's)."""
         import torch
@@ -138,7 +141,7 @@ class DeviceSim:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.L = lib()
         self.precision = precision
-        self.cfg = config_of(world, precision, write_aux, n_replicas, agent_car)
+        self.cfg = config_of(world, precision, write_aux, n_replicas, agent_car, neighbor_mode)
         self.n_replicas = int(n_replicas)
         self._switch_time, self._face_go = switch_time, face_go
         self.n_cars, self.n_lights, self.n_faces = world.n_cars, world.n_lights, world.n_faces
