@@ -146,6 +146,18 @@ int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stre
 int tb2_step_host(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
                   void* frame_xy_out, uint8_t* face_go_out, void* stream);
 
+/* Init-time routing (the producer of the hot path's inputs): for every (origin, destination) pair the
+ * shortest path by edge weight, i.e. networkx.shortest_path(G, o, d, weight='length') as navigation.get_route /
+ * get_init_path / lines_to_node call it once per car and per light face (navigation.py:581-609, 764-841).  The graph is
+ * a CSR over node indices 0..n_nodes-1 (host arrays; parallel edges allowed, the shortest one wins as in
+ * navigation.py:820).  Writes the node sequence origin..destination of pair p to path_nodes[p*max_len ...] and its length
+ * to path_len[p] (-1: no path = networkx.NetworkXNoPath, -2: longer than max_len).  limit < 0: unbounded search, else
+ * nodes farther than `limit` from the origin are not explored.  Synchronous. */
+int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
+                    int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit, int32_t max_len,
+                    int32_t* path_len, int32_t* path_nodes, void* stream);
+const char* tb2_route_last_error(void);
+
 /* number of kernel launches issued by this sim so far (bench.py's gpu_launches) */
 int64_t tb2_launch_count(const tb2_sim* sim);
 int64_t tb2_step_count(const tb2_sim* sim);

@@ -1,0 +1,89 @@
+"""Init-time routing: the GPU batched shortest-path search against the routes the reference itself
+produced (golden fixtures: networkx.shortest_path inside sim.init_random_node_start_location) and against scipy."""
+import numpy as np
+import pytest
+
+from tests import util
+from traffic_b200 import routing, synth
+
+
+def _graph_of(name):
+    from oracle.ref_harness import CONFIGS   # test infrastructure; importing it does not touch /root/reference
+    return synth.SynthGraph(**CONFIGS[name]["g"])
+
+
+def test_polylines_drop_duplicates_and_empty_routes():
+    node_xy = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 0.0], [2.0, 5.0]])
+    path_len = np.array([4, 1, -1, 2], np.int32)
+    path_nodes = np.array([[0, 1, 2, 3], [2, 0, 0, 0], [0, 0, 0, 0], [3, 0, 0, 0]], np.int32)
+    ptr, xy = routing.polylines(node_xy, path_len, path_nodes)
+    assert ptr.tolist() == [0, 3, 3, 3, 5]                       # duplicate point dropped; 1-node and no-path routes empty
+    assert xy.tolist() == [[0.0, 0.0], [1.0, 0.0], [2.0, 5.0], [2.0, 5.0], [0.0, 0.0]]
+
+
+def test_csr_of_keeps_parallel_edges():
+    indptr, indices, w = routing.csr_of(3, [0, 0, 1, 0], [1, 2, 2, 1], [5.0, 1.0, 1.0, 2.0])
+    assert indptr.tolist() == [0, 3, 4, 4] and indices.tolist() == [1, 2, 1, 2] and w.tolist() == [5.0, 1.0, 2.0, 1.0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_dt0.001_p2_s1", "dense_dt0.001_p2_s3", "c2_dt0.001_p10_s0"])
+def test_gpu_routes_equal_reference_routes(name):
+    g = util.load_golden(name)
+    graph = _graph_of(name)
+    # recover (origin, destination) node indices from the fixture's coordinates
+    key = {tuple(p): i for i, p in enumerate(graph.node_xy)}
+    origin = np.array([key[tuple(p)] for p in g["pos0"]], np.int32)
+    dest = np.array([key[tuple(p)] for p in g["dest_xy"]], np.int32)
+    indptr, indices, w = routing.csr_of(graph.n_nodes, graph.edge_u, graph.edge_v, graph.edge_len)
+    path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origin, dest)
+    ptr, xy = routing.polylines(graph.node_xy, path_len, path_nodes)
+    assert np.array_equal(ptr, g["path_ptr"]), "polyline lengths differ from the reference's routes"
+    assert np.array_equal(xy, g["path_xy"]), "polyline points differ from the reference's routes"
+    assert (path_len == 1).sum() == (np.diff(g["path_ptr"]) == 0).sum()   # origin == destination -> empty route
+
+
+@pytest.mark.gpu
+def test_gpu_routes_equal_scipy_on_random_graph():
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+    rng = np.random.default_rng(5)
+    n, m = 3000, 14000
+    u, v = rng.integers(0, n, m), rng.integers(0, n, m)
+    keep = u != v
+    u, v = u[keep], v[keep]
+    wts = rng.uniform(1.0, 100.0, len(u))
+    indptr, indices, w = routing.csr_of(n, u, v, wts)
+    origin = rng.integers(0, 40, 500).astype(np.int32)        # 40 distinct sources
+    dest = rng.integers(0, n, 500).astype(np.int32)
+    path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origin, dest, max_len=64)
+    # scipy keeps the minimum of parallel edges when the matrix is built with duplicates summed -> build min explicitly
+    best = {}
+    for a, b, c in zip(u, v, wts):
+        best[(a, b)] = min(best.get((a, b), np.inf), c)
+    rows, cols = zip(*best.keys())
+    mat = csr_matrix((list(best.values()), (rows, cols)), shape=(n, n))
+    srcs = np.unique(origin)
+    dist, pred = dijkstra(mat, directed=True, indices=srcs, return_predecessors=True)
+    row_of = {s: i for i, s in enumerate(srcs)}
+    for p in range(len(origin)):
+        r = row_of[origin[p]]
+        if not np.isfinite(dist[r, dest[p]]):
+            assert path_len[p] == -1
+            continue
+        want = [dest[p]]
+        while want[-1] != origin[p]:
+            want.append(pred[r, want[-1]])
+        want = want[::-1]
+        assert path_len[p] == len(want) and path_nodes[p, :len(want)].tolist() == [int(x) for x in want]
+
+
+@pytest.mark.gpu
+def test_routing_limit_and_errors():
+    from traffic_b200 import native
+    graph = synth.SynthGraph(20, 20, seed=1)
+    indptr, indices, w = routing.csr_of(graph.n_nodes, graph.edge_u, graph.edge_v, graph.edge_len)
+    pl, _ = routing.shortest_paths(indptr, indices, w, [0, 0], [1, 399], limit=500.0)
+    assert pl[0] == 2 and pl[1] == -1          # the far corner is outside the search radius
+    with pytest.raises(native.NativeError):
+        routing.shortest_paths(indptr, indices, w, [0], [400])

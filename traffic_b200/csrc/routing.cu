@@ -1,0 +1,210 @@
+// Batched shortest-path routing on the device - the init-time producer of the hot path's inputs.
+//
+// Replaces, for a batch of (origin, destination) pairs, networkx.shortest_path(G, o, d, weight='length') as the
+// reference calls it once per car and once per light face (navigation.get_route / get_init_path /
+// shortest_path_lines_nx / lines_to_node, navigation.py:581-609, 764-841; simulation.py:217-219; about 16 ms per car in
+// the reference).  One CTA per distinct origin runs a label-correcting (Bellman-Ford style) single-source search on the
+// CSR graph with 64-bit atomicMin on the distance bit patterns (non-negative doubles order like their bit patterns), then
+// a predecessor pass and a per-pair walk emit the node sequences.  Distances satisfy the same recurrence Dijkstra
+// evaluates, dist[v] = min_u fl(dist[u] + w(u, v)), so the chosen predecessors - and hence the routes - are the ones
+// networkx returns whenever the shortest path is unique (ties are measure-zero on real-valued edge lengths; the parity
+// tests compare against the routes the reference itself produced).
+#include "../../include/traffic_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr unsigned long long kInfBits = 0x7ff0000000000000ull;  // +inf
+
+__global__ void __launch_bounds__(256) sssp_kernel(int n_nodes, const int32_t* __restrict__ indptr,
+                                                   const int32_t* __restrict__ indices, const double* __restrict__ weight,
+                                                   const int32_t* __restrict__ sources, double limit,
+                                                   unsigned long long* dist_all, int32_t* pred_all) {
+    __shared__ int changed;
+    const int s = blockIdx.x;
+    unsigned long long* dist = dist_all + (size_t)s * n_nodes;
+    int32_t* pred = pred_all + (size_t)s * n_nodes;
+    const int src = sources[s];
+    for (int u = threadIdx.x; u < n_nodes; u += 256) {
+        dist[u] = (u == src) ? 0ull : kInfBits;
+        pred[u] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < n_nodes; ++sweep) {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        int my_changed = 0;
+        for (int u = threadIdx.x; u < n_nodes; u += 256) {
+            const unsigned long long dub = *(volatile unsigned long long*)&dist[u];
+            if (dub == kInfBits) continue;
+            const double du = __longlong_as_double((long long)dub);
+            for (int e = indptr[u]; e < indptr[u + 1]; ++e) {
+                const double nd = __dadd_rn(du, weight[e]);
+                if (nd > limit) continue;
+                const unsigned long long nb = (unsigned long long)__double_as_longlong(nd);
+                const int v = indices[e];
+                if (nb < *(volatile unsigned long long*)&dist[v]) {
+                    if (atomicMin(&dist[v], nb) > nb) my_changed = 1;
+                }
+            }
+        }
+        if (my_changed) changed = 1;
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    // predecessor of v: the node u with fl(dist[u] + w(u, v)) == dist[v] (smallest u on an exact tie)
+    for (int u = threadIdx.x; u < n_nodes; u += 256) {
+        const unsigned long long dub = dist[u];
+        if (dub == kInfBits) continue;
+        const double du = __longlong_as_double((long long)dub);
+        for (int e = indptr[u]; e < indptr[u + 1]; ++e) {
+            const int v = indices[e];
+            if (v == src) continue;
+            const double nd = __dadd_rn(du, weight[e]);
+            if ((unsigned long long)__double_as_longlong(nd) == dist[v]) atomicMin(&pred[v], u);
+        }
+    }
+}
+
+// one thread per (origin, destination) pair: walk the predecessors back from the destination, then reverse
+__global__ void __launch_bounds__(128) extract_paths_kernel(int n_pairs, int n_nodes, const int32_t* __restrict__ pair_source_slot,
+                                                            const int32_t* __restrict__ origin, const int32_t* __restrict__ dest,
+                                                            const unsigned long long* __restrict__ dist_all,
+                                                            const int32_t* __restrict__ pred_all, int max_len,
+                                                            int32_t* __restrict__ path_len, int32_t* __restrict__ path_nodes) {
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= n_pairs) return;
+    const size_t base = (size_t)pair_source_slot[p] * n_nodes;
+    int32_t* out = path_nodes + (size_t)p * max_len;
+    const int o = origin[p], d = dest[p];
+    if (dist_all[base + d] == kInfBits) { path_len[p] = -1; return; }   // networkx.NetworkXNoPath
+    int len = 0, cur = d;
+    while (true) {
+        if (len >= max_len) { path_len[p] = -2; return; }                // caller's buffer too short
+        out[len++] = cur;
+        if (cur == o) break;
+        cur = pred_all[base + cur];
+        if (cur == 0x7fffffff) { path_len[p] = -1; return; }
+    }
+    for (int a = 0, b = len - 1; a < b; ++a, --b) { const int t = out[a]; out[a] = out[b]; out[b] = t; }
+    path_len[p] = len;
+}
+
+thread_local std::string g_route_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* tb2_route_last_error(void) { return g_route_err.c_str(); }
+
+// CSR graph on node indices 0..n_nodes-1 (host arrays).  For every pair p writes the node sequence origin..destination
+// to path_nodes[p*max_len ...] and its length to path_len[p] (-1: no path, -2: longer than max_len).  `limit` < 0 means
+// unbounded search; otherwise nodes farther than `limit` from the origin are not explored.  Synchronous.
+int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
+                    int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit, int32_t max_len,
+                    int32_t* path_len, int32_t* path_nodes, void* stream_) {
+#define RCU(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) { g_route_err = std::string(#call) + ": " + cudaGetErrorString(e__); rc = TB2_ERR_CUDA; goto done; } \
+    } while (0)
+    if (n_nodes <= 0 || n_pairs < 0 || max_len <= 0 || !indptr || !indices || !weight) {
+        g_route_err = "tb2_route_paths: bad argument";
+        return TB2_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        g_route_err = "no CUDA device available - traffic_b200 has no CPU path";
+        return TB2_ERR_NO_DEVICE;
+    }
+    if (n_pairs == 0) return TB2_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = TB2_OK;
+    // distinct origins -> source slots
+    std::vector<int32_t> slot_of_node(n_nodes, -1), sources, pair_slot(n_pairs);
+    for (int p = 0; p < n_pairs; ++p) {
+        const int o = origin[p];
+        if (o < 0 || o >= n_nodes || dest[p] < 0 || dest[p] >= n_nodes) { g_route_err = "node index out of range"; return TB2_ERR_INVALID; }
+        if (slot_of_node[o] < 0) { slot_of_node[o] = (int32_t)sources.size(); sources.push_back(o); }
+        pair_slot[p] = slot_of_node[o];
+    }
+    const int n_edges = indptr[n_nodes];
+    const double lim = limit < 0 ? __builtin_inf() : limit;
+    // chunk the sources so that dist + pred stay under ~2 GB
+    const size_t per_source = (size_t)n_nodes * 12;
+    size_t chunk_sz = ((size_t)2 << 30) / (per_source > 0 ? per_source : 1);
+    if (chunk_sz < 1) chunk_sz = 1;
+    int chunk = chunk_sz > (size_t)1 << 20 ? 1 << 20 : (int)chunk_sz;
+    if (chunk > (int)sources.size()) chunk = (int)sources.size();
+    int32_t *d_indptr = nullptr, *d_indices = nullptr, *d_sources = nullptr, *d_pred = nullptr, *d_pair_slot = nullptr,
+            *d_origin = nullptr, *d_dest = nullptr, *d_len = nullptr, *d_nodes = nullptr;
+    double* d_weight = nullptr;
+    unsigned long long* d_dist = nullptr;
+    std::vector<int32_t> sel_pairs, sel_slot, sel_o, sel_d, tmp_len, tmp_nodes;
+    RCU(cudaMalloc(&d_indptr, sizeof(int32_t) * (n_nodes + 1)));
+    RCU(cudaMalloc(&d_indices, sizeof(int32_t) * (n_edges > 0 ? n_edges : 1)));
+    RCU(cudaMalloc(&d_weight, sizeof(double) * (n_edges > 0 ? n_edges : 1)));
+    RCU(cudaMalloc(&d_sources, sizeof(int32_t) * chunk));
+    RCU(cudaMalloc(&d_dist, sizeof(unsigned long long) * (size_t)chunk * n_nodes));
+    RCU(cudaMalloc(&d_pred, sizeof(int32_t) * (size_t)chunk * n_nodes));
+    RCU(cudaMemcpyAsync(d_indptr, indptr, sizeof(int32_t) * (n_nodes + 1), cudaMemcpyDefault, stream));
+    RCU(cudaMemcpyAsync(d_indices, indices, sizeof(int32_t) * n_edges, cudaMemcpyDefault, stream));
+    RCU(cudaMemcpyAsync(d_weight, weight, sizeof(double) * n_edges, cudaMemcpyDefault, stream));
+    {
+        // pairs grouped by source chunk
+        std::vector<std::vector<int32_t>> by_chunk((sources.size() + chunk - 1) / chunk);
+        for (int p = 0; p < n_pairs; ++p) by_chunk[pair_slot[p] / chunk].push_back(p);
+        size_t max_pairs = 0;
+        for (auto& v : by_chunk) max_pairs = v.size() > max_pairs ? v.size() : max_pairs;
+        RCU(cudaMalloc(&d_pair_slot, sizeof(int32_t) * max_pairs));
+        RCU(cudaMalloc(&d_origin, sizeof(int32_t) * max_pairs));
+        RCU(cudaMalloc(&d_dest, sizeof(int32_t) * max_pairs));
+        RCU(cudaMalloc(&d_len, sizeof(int32_t) * max_pairs));
+        RCU(cudaMalloc(&d_nodes, sizeof(int32_t) * max_pairs * (size_t)max_len));
+        for (size_t c = 0; c < by_chunk.size(); ++c) {
+            const int s0 = (int)c * chunk;
+            const int ns = (int)sources.size() - s0 < chunk ? (int)sources.size() - s0 : chunk;
+            const auto& pairs = by_chunk[c];
+            if (pairs.empty()) continue;
+            RCU(cudaMemcpyAsync(d_sources, sources.data() + s0, sizeof(int32_t) * ns, cudaMemcpyDefault, stream));
+            sssp_kernel<<<ns, 256, 0, stream>>>(n_nodes, d_indptr, d_indices, d_weight, d_sources, lim, d_dist, d_pred);
+            RCU(cudaGetLastError());
+            const int np = (int)pairs.size();
+            sel_slot.resize(np); sel_o.resize(np); sel_d.resize(np);
+            for (int k = 0; k < np; ++k) {
+                sel_slot[k] = pair_slot[pairs[k]] - s0; sel_o[k] = origin[pairs[k]]; sel_d[k] = dest[pairs[k]];
+            }
+            RCU(cudaMemcpyAsync(d_pair_slot, sel_slot.data(), sizeof(int32_t) * np, cudaMemcpyDefault, stream));
+            RCU(cudaMemcpyAsync(d_origin, sel_o.data(), sizeof(int32_t) * np, cudaMemcpyDefault, stream));
+            RCU(cudaMemcpyAsync(d_dest, sel_d.data(), sizeof(int32_t) * np, cudaMemcpyDefault, stream));
+            extract_paths_kernel<<<(np + 127) / 128, 128, 0, stream>>>(np, n_nodes, d_pair_slot, d_origin, d_dest, d_dist, d_pred,
+                                                                       max_len, d_len, d_nodes);
+            RCU(cudaGetLastError());
+            tmp_len.resize(np); tmp_nodes.resize((size_t)np * max_len);
+            RCU(cudaMemcpyAsync(tmp_len.data(), d_len, sizeof(int32_t) * np, cudaMemcpyDefault, stream));
+            RCU(cudaMemcpyAsync(tmp_nodes.data(), d_nodes, sizeof(int32_t) * (size_t)np * max_len, cudaMemcpyDefault, stream));
+            RCU(cudaStreamSynchronize(stream));
+            for (int k = 0; k < np; ++k) {
+                const int p = pairs[k];
+                path_len[p] = tmp_len[k];
+                const int n = tmp_len[k] > 0 ? tmp_len[k] : 0;
+                for (int q = 0; q < n; ++q) path_nodes[(size_t)p * max_len + q] = tmp_nodes[(size_t)k * max_len + q];
+            }
+        }
+    }
+done:
+    cudaFree(d_indptr); cudaFree(d_indices); cudaFree(d_weight); cudaFree(d_sources); cudaFree(d_dist); cudaFree(d_pred);
+    cudaFree(d_pair_slot); cudaFree(d_origin); cudaFree(d_dest); cudaFree(d_len); cudaFree(d_nodes);
+    return rc;
+#undef RCU
+}
+
+}  // extern "C"
