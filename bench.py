@@ -355,7 +355,9 @@ def main():
                        "path_points": int(len(w.path_xy)), "cells": w.grid.n_cells, "dt": dt,
                        "order": "cars_then_lights", "replicas": world, "parallelism": "replica-per-gpu",
                        "neighbor": args.neighbor,
-                       "l2": "working set %.0f MB per step > %.0f MB L2, no explicit flush" % (ws / 1e6, L2_BYTES / 1e6),
+                       "l2": ("working set %.0f MB per step > %.0f MB L2, no explicit flush" if ws > L2_BYTES else
+                              "working set %.0f MB per step FITS the %.0f MB L2 and is not flushed (state is resident by design)")
+                             % (ws / 1e6, L2_BYTES / 1e6),
                        "frame_every_k_steps": k},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "step_kernel<%s>" % ("double" if prec == native.F64 else "float"),
