@@ -281,6 +281,11 @@ __device__ __forceinline__ void lights_tick_body(int lg, int n_lights_total, int
 }
 
 __device__ __forceinline__ void table_insert(int32_t* tab, int cell, int i) {
+    // Entries only ever decrease while a table is being filled, so a car whose index already exceeds the bin's current
+    // second-smallest entry can never end up among the first two: it skips both atomics.  CTAs run roughly in index
+    // order, so after the first couple of cars of a bin almost everybody skips - no same-address serialisation in L2 and
+    // no wait for the atomic's return value.  (The read bypasses L1; a stale value is only larger, i.e. conservative.)
+    if (i > __ldcg(&tab[2 * cell + 1])) return;
     const int old = atomicMin(&tab[2 * cell], i);
     const int loser = old > i ? old : i;   // whoever is not the cell minimum competes for second place
     if (loser != TB2_EMPTY) atomicMin(&tab[2 * cell + 1], loser);
