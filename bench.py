@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -372,13 +372,13 @@ def main():
         }
         if rollout is not None:
             line["rollout"] = rollout
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
             v, s_, t_ = cpu_port_updates_per_s(w, dt, order, args.cpu_budget, threads=1)
             line["cpu_baseline"] = {"value": v, "unit": "vehicle-updates/s", "cores": 1, "kind": "port",
                                     "sample": "%d steps of the same %d-car workload (%.1f s), C oracle port, 1 thread; "
                                               "the unmodified Python reference runs 300-450 updates/s on one core"
                                               % (s_, w.n_cars, t_)}
-        if not args.no_small and args.workload != "c2_manhattan_2k":
+        if not args.no_small and args.workload != "c2_manhattan_2k" and world == 1:
             w2 = make_workload("c2_manhattan_2k", args.seed)
             s2 = native.DeviceSim(w2, precision=prec)
             s2.step(dt, 200, order)
@@ -392,7 +392,7 @@ def main():
             line["also"] = {"workload": "c2_manhattan_2k", "cars": w2.n_cars, "steps": 2000,
                             "value": w2.n_cars * 2000 / (ms2 * 1e-3), "unit": "vehicle-updates/s",
                             "us_per_step": ms2 / 2000 * 1e3}
-        if not args.no_small:
+        if not args.no_small and world == 1:
             try:
                 line["also_facade"] = facade_profile_loop()
             except Exception as e:  # the headline must not depend on the secondary measurement
