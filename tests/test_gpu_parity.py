@@ -252,3 +252,27 @@ def test_sort_neighbour_source_equals_atomic_table(replicas):
             sim.download_world(w)
             ok, _ = util.compare_step(util.snapshot(w, start), g, t, w.grid.ncx, FLOAT_RTOL, report)
             assert ok, "\\n".join(report[:5])
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_persistent_cluster_kernel_equals_per_step_launches(order, monkeypatch):
+    """Small worlds run a whole tb2_step batch in one launch (thread-block cluster + cluster barrier per step); it must
+    be indistinguishable from one launch per step, for both call orders, odd and even batch lengths, with aux columns."""
+    native = _native()
+    from traffic_b200 import synth
+
+    w0, _ = synth.make_city(nx_=40, ny_=40, n_cars=3500, prescale=3, seed=51, max_hops=12)
+    outs = []
+    for no_persist in ("1", "0"):
+        monkeypatch.setenv("TB2_NO_PERSISTENT", no_persist)
+        w = w0.copy()
+        sim = native.DeviceSim(w)
+        launches0 = sim.launch_count
+        for n in (7, 100, 1, 250, 33):
+            sim.step(1e-3, n, order)
+        outs.append((sim.download_world(w), sim.launch_count - launches0))
+    (a, la), (b, lb) = outs
+    assert lb < 10 < la, "persistent path not taken (launches %d vs %d)" % (lb, la)
+    for f in ("pos", "vel", "route_time", "cursor", "d_node", "d_car", "d_light", "cell", "leader", "face_go"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+    assert a.lights_time == b.lights_time and (a.leader >= 0).sum() > 20

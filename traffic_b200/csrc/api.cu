@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -130,6 +131,7 @@ struct tb2_sim {
     int n_cells = 0;
     int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
+    bool allow_persistent = true;   // TB2_NO_PERSISTENT=1 in the environment forces one launch per step (A/B testing)
     int64_t launches = 0, steps = 0;
     double log_free_over_stop = 0.0;
 
@@ -262,6 +264,26 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
                                            s->buf<char>(B_SORT_TEMP), s->lay.bytes[B_SORT_TEMP], a.tab_next, stream);
 }
 
+// All n_steps of a batch in one launch of the persistent cluster kernel (small worlds only).
+template <typename R>
+cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cudaStream_t stream) {
+    using R2 = typename real2<R>::type;
+    const size_t C2 = (size_t)2 * s->n_cells * s->cfg.n_replicas;
+    StepArgsT<R> a{};
+    fill_args<R>(s, &a);
+    a.dt = (R)dt;
+    a.dt64 = dt;
+    a.skip_insert = 0;
+    PersistArgsT<R> pa{};
+    pa.pos[0] = s->buf<R2>(B_POS0); pa.pos[1] = s->buf<R2>(B_POS1);
+    for (int k = 0; k < 3; ++k) pa.tab[k] = s->buf<int32_t>(B_TAB) + C2 * k;
+    pa.go[0] = s->buf<uint8_t>(B_GO0); pa.go[1] = s->buf<uint8_t>(B_GO1);
+    pa.t[0] = s->buf<double>(B_T0); pa.t[1] = s->buf<double>(B_T1);
+    pa.cur_pos = s->cur_pos; pa.cur_tab = s->cur_tab; pa.cur_go = s->cur_go; pa.cur_t = s->cur_t;
+    pa.n_steps = n_steps; pa.order = order; pa.aux_last = s->cfg.write_aux;
+    return launch_persistent(a, pa, stream);
+}
+
 // Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
 // aux: also write the columns nobody can observe between steps (velocity, distances, leader, start-of-step bin).
 void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
@@ -303,6 +325,7 @@ int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_s
     s->lay = make_layout(*cfg);
     s->n_cells = (cfg->nbx + 1) * (cfg->nby + 1);
     s->log_free_over_stop = std::log(cfg->free_distance / cfg->stop_distance);  // host libm, simulation.py:180
+    if (const char* np = std::getenv("TB2_NO_PERSISTENT")) s->allow_persistent = !(np[0] == '1');
     if (arena_dev) {
         if (arena_bytes < s->lay.total) { delete s; return fail(TB2_ERR_INVALID, "arena too small (see tb2_arena_bytes)"); }
         if (reinterpret_cast<uintptr_t>(arena_dev) % kAlign) { delete s; return fail(TB2_ERR_INVALID, "arena must be 256-byte aligned"); }
@@ -415,6 +438,20 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
     if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
     if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (state was uploaded since)");
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (s->allow_persistent && n_steps >= 2 && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC &&
+        (int64_t)s->cfg.n_cars * s->cfg.n_replicas <= persistent_max_cars()) {
+        // small world: the whole batch is one launch of the persistent cluster kernel
+        CU(s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, n_steps, order, stream)
+                                       : step_persistent_t<float>(s, dt, n_steps, order, stream));
+        s->launches++;
+        s->cur_pos ^= (n_steps & 1);
+        s->cur_tab = (s->cur_tab + n_steps) % 3;
+        s->cur_go ^= (n_steps & 1);      // n_steps ticks in either order
+        s->cur_t ^= (n_steps & 1);
+        s->steps += n_steps;
+        CU(cudaGetLastError());
+        return TB2_OK;
+    }
     for (int32_t k = 0; k < n_steps; ++k) {
         // lights-first order: L (C L) (C L) ... C - the first tick is its own launch, the rest ride in the step kernel
         if (order == TB2_ORDER_LIGHTS_CARS && k == 0) tick_lights(s, dt, stream);

@@ -89,12 +89,26 @@ struct StepArgsT {
     int32_t* trip_step;
 };
 
+// Extra arguments of the persistent small-world kernel: every rotating buffer and where the rotation stands.
+template <typename R>
+struct PersistArgsT {
+    typename real2<R>::type* pos[2];
+    int32_t* tab[3];
+    uint8_t* go[2];
+    double* t[2];
+    int32_t cur_pos, cur_tab, cur_go, cur_t;
+    int32_t n_steps, order, aux_last, pad;
+};
+
 using StepArgs64 = StepArgsT<double>;
 using StepArgs32 = StepArgsT<float>;
 
 int step_block_threads();
 void launch_step(const StepArgs64& a, cudaStream_t stream);
 void launch_step(const StepArgs32& a, cudaStream_t stream);
+int persistent_max_cars();
+cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream);
+cudaError_t launch_persistent(const StepArgs32& a, const PersistArgsT<float>& pa, cudaStream_t stream);
 // (re)derive everything the step kernel keeps cached from the uploaded state: per-point curvature constants, per-car
 // head point + constants, unit face vectors, bins, and the cell table `cur_table` of the three in tab3 (all reset).
 void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3, int cur_table,

@@ -17,6 +17,11 @@ int step_block_threads() { return TB2_BLOCK; }
 
 void launch_step(const StepArgs64& a, cudaStream_t stream) { tb2k::launch_step_t<double>(a, stream); }
 
+int persistent_max_cars() { return TB2_PERSIST_BLOCK * TB2_PERSIST_MAX_CTAS; }
+cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream) {
+    return tb2k::launch_persistent_t<double>(a, pa, stream);
+}
+
 void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3, int cur_table,
                     cudaStream_t stream) {
     tb2k::launch_prepare_t<double>(a, pt_curv, face_unit, n_faces, tab3, cur_table, stream);

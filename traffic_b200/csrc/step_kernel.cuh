@@ -31,6 +31,7 @@
 #pragma once
 #include "step_args.cuh"
 
+#include <cooperative_groups.h>
 #include <math_constants.h>
 #include <type_traits>
 
@@ -40,6 +41,9 @@
 #ifndef TB2_BLOCK
 #define TB2_BLOCK 128   // threads per CTA of the step kernel (cars per CTA)
 #endif
+#define TB2_PERSIST_BLOCK 256      // threads per CTA of the persistent small-world kernel
+#define TB2_PERSIST_MAX_CTAS 16    // one thread-block cluster (16 needs the non-portable-size opt-in)
+#define TB2K_ORDER_LIGHTS_CARS 1
 
 namespace tb2k {
 
@@ -244,12 +248,13 @@ static __device__ __noinline__ bool antiparallel_exact(double cvx, double cvy, d
     return isclose_<double>(K<double>::pi, acos(c), 1.0e-5, 0.1);
 }
 template <typename R>
-__device__ __forceinline__ bool red_face_ahead(const StepArgsT<R>& a, int fb, int fe, int fbase, R cvx, R cvy) {
+__device__ __forceinline__ bool red_face_ahead(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fb, int fe,
+                                               int fbase, R cvx, R cvy) {
     const float fx = (float)cvx, fy = (float)cvy;
     const float inv = rsqrtf(fx * fx + fy * fy);
     bool found = false;
     for (int f = fb; f < fe && !found; ++f) {
-        if (a.go_cur[fbase + f]) continue;
+        if (go_cur[fbase + f]) continue;
         const typename real2<R>::type fu = a.face_unit[f];
         const float c = (fx * (float)fu.x + fy * (float)fu.y) * inv;
         if constexpr (is_f64<R>) {
@@ -291,27 +296,28 @@ __device__ __forceinline__ void table_insert(int32_t* tab, int cell, int i) {
     if (loser != TB2_EMPTY) atomicMin(&tab[2 * cell + 1], loser);
 }
 
-// AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell tables / face states, agent
-// arrival bookkeeping); a single simulation compiles these out.
+// The buffers that rotate from step to step (ping-pong positions, the three cell tables, double-buffered faces).
+template <typename R>
+struct Rot {
+    const typename real2<R>::type* pos_in;
+    typename real2<R>::type* pos_out;
+    const int2* tab_cur;
+    int32_t* tab_next;
+    const uint8_t* go_cur;
+    int32_t step_index;
+};
+
+// One car, one step.  AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell tables /
+// face states, agent arrival bookkeeping); a single simulation compiles these out.
 template <typename R, bool AUX, bool ENS>
-__global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const __grid_constant__ StepArgsT<R> a) {
+__device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& rot, const int i) {
     using R2 = typename real2<R>::type;
-    if ((int)blockIdx.x >= a.car_blocks) {
-        const int l = ((int)blockIdx.x - a.car_blocks) * TB2_BLOCK + (int)threadIdx.x;
-        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
-                         a.go_cur, a.go_next, a.t_cur, a.t_next);
-        return;
-    }
-    const int i = (int)blockIdx.x * TB2_BLOCK + (int)threadIdx.x;
-    // reset the table that the launch after next will fill
-    for (int k = i; k < 2 * a.g.n_cells * a.n_replicas; k += a.car_blocks * TB2_BLOCK) a.tab_clear[k] = TB2_EMPTY;
-    if (i >= a.n_cars) return;
     // replica of this car (1 for a single simulation): offsets into the per-replica cell tables and face states
     const int rep = ENS ? i / a.cars_per_replica : 0;
     const int cbase = rep * a.g.n_cells, fbase = rep * a.faces_per_replica, ibase = rep * a.cars_per_replica;
 
     // ---- independent loads first ----
-    const R2 p = a.pos_in[i];
+    const R2 p = rot.pos_in[i];
     const int cur = a.cursor[i];
     const int end = a.path_end[i];
     const int eff = a.path_eff_end[i];
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
     const R2 hc = a.head_curv[i];
     const R rt = a.route_time[i];
     // ---- dependent on the bin ----
-    const int2 m = a.tab_cur[cbase + c];
+    const int2 m = rot.tab_cur[cbase + c];
     const CellLightsT<R> cl = a.cell_lights[c];
     const int lb = cl.lb, le = cl.lb + (cl.counts & 0xffff);
 
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
     int lead = -1;
     const int j = (m.x != i) ? m.x : m.y;
     if (spaces && j != TB2_EMPTY) {
-        const R2 o = a.pos_in[j];
+        const R2 o = rot.pos_in[j];
         if (on_axis(ax, 0, o.x, a.origin_x) && on_axis(ay, 0, o.y, a.origin_y)) {
             d_car = norm2<R>(o.x - x, o.y - y);
             if (d_car != R(0)) lead = j;
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
                 const R cvx = lp.x - x, cvy = lp.y - y;
                 const int fb = (q == lb) ? cl.fb0 : a.face_ptr[l];
                 const int fe = (q == lb) ? cl.fb0 + (cl.counts >> 16) : a.face_ptr[l + 1];
-                if (red_face_ahead<R>(a, fb, fe, fbase, cvx, cvy)) { d_light = norm2<R>(cvx, cvy); break; }
+                if (red_face_ahead<R>(a, rot.go_cur, fb, fe, fbase, cvx, cvy)) { d_light = norm2<R>(cvx, cvy); break; }
             } else { d_light = R(0); break; }
         }
     }
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
         a.cursor[i] = end;  // path becomes []
     }
     const R xn = x + vx * a.dt, yn = y + vy * a.dt;  // cars.py:89-90
-    a.pos_out[i] = mk2(xn, yn);
+    rot.pos_out[i] = mk2(xn, yn);
     if (AUX) {
         a.vel[i] = mk2(vx, vy);
         a.d_node[i] = d_node;
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
     if (cn != c) a.cell[i] = cn;
-    if (!a.skip_insert) table_insert(a.tab_next, cbase + cn, i);
+    if (!a.skip_insert) table_insert(rot.tab_next, cbase + cn, i);
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
@@ -435,8 +441,67 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
         if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
             a.done[rep] = 1;
             a.trip_time[rep] = (double)rt;
-            a.trip_step[rep] = a.step_index;
+            a.trip_step[rep] = rot.step_index;
         }
+    }
+}
+
+// One launch per step: CTAs [0, car_blocks) take one car per thread, the trailing CTAs tick the lights.
+template <typename R, bool AUX, bool ENS>
+__global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const __grid_constant__ StepArgsT<R> a) {
+    if ((int)blockIdx.x >= a.car_blocks) {
+        const int l = ((int)blockIdx.x - a.car_blocks) * TB2_BLOCK + (int)threadIdx.x;
+        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
+                         a.go_cur, a.go_next, a.t_cur, a.t_next);
+        return;
+    }
+    const int i = (int)blockIdx.x * TB2_BLOCK + (int)threadIdx.x;
+    // reset the table that the launch after next will fill
+    for (int k = i; k < 2 * a.g.n_cells * a.n_replicas; k += a.car_blocks * TB2_BLOCK) a.tab_clear[k] = TB2_EMPTY;
+    if (i >= a.n_cars) return;
+    const Rot<R> rot{a.pos_in, a.pos_out, a.tab_cur, a.tab_next, a.go_cur, a.step_index};
+    step_car<R, AUX, ENS>(a, rot, i);
+}
+
+// Small worlds (<= 4096 cars): ALL steps of a tb2_step batch in ONE launch.  The CTAs form a single thread-block cluster
+// and meet at a hardware cluster barrier (release/acquire, so the positions, table entries and face states written in
+// step s are visible to every CTA in step s+1) instead of returning to the host between steps - at 2k cars a step is a
+// single wave of warps and the per-launch gap is a third of the step time.
+template <typename R, bool ENS>
+__global__ void __launch_bounds__(TB2_PERSIST_BLOCK, 1) persistent_kernel(const __grid_constant__ StepArgsT<R> a,
+                                                                          const __grid_constant__ PersistArgsT<R> pa) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nthreads = (int)(gridDim.x * blockDim.x);
+    const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int n_tab = 2 * a.g.n_cells * a.n_replicas;
+    const int n_tick = a.n_lights > 0 ? a.n_lights : 1;   // thread 0 advances the clock even without lights
+    int cp = pa.cur_pos, ct = pa.cur_tab, cgo = pa.cur_go, ck = pa.cur_t;
+    if (pa.order == TB2K_ORDER_LIGHTS_CARS) {               // L (C L) (C L) ... C
+        for (int lg = gtid; lg < n_tick; lg += nthreads)
+            lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
+                             pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1]);
+        cgo ^= 1; ck ^= 1;
+        cluster.sync();
+    }
+    for (int s = 0; s < pa.n_steps; ++s) {
+        const bool tick = pa.order != TB2K_ORDER_LIGHTS_CARS || s < pa.n_steps - 1;
+        int32_t* tab_clear = pa.tab[(ct + 2) % 3];
+        for (int k = gtid; k < n_tab; k += nthreads) tab_clear[k] = TB2_EMPTY;
+        if (gtid < a.n_cars) {
+            const Rot<R> rot{pa.pos[cp], pa.pos[cp ^ 1], reinterpret_cast<const int2*>(pa.tab[ct]), pa.tab[(ct + 1) % 3],
+                             pa.go[cgo], a.step_index + s};
+            if (pa.aux_last && s == pa.n_steps - 1) step_car<R, true, ENS>(a, rot, gtid);
+            else step_car<R, false, ENS>(a, rot, gtid);
+        }
+        if (tick) {
+            for (int lg = gtid; lg < n_tick; lg += nthreads)
+                lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time,
+                                 a.face_ptr, pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1]);
+            cgo ^= 1; ck ^= 1;
+        }
+        cp ^= 1; ct = (ct + 1) % 3;
+        cluster.sync();
     }
 }
 
@@ -526,6 +591,28 @@ void launch_step_t(const StepArgsT<R>& a, cudaStream_t stream) {
         if (a.write_aux) step_kernel<R, true, false><<<grid, TB2_BLOCK, 0, stream>>>(a);
         else step_kernel<R, false, false><<<grid, TB2_BLOCK, 0, stream>>>(a);
     }
+}
+
+template <typename R>
+cudaError_t launch_persistent_t(const StepArgsT<R>& a, const PersistArgsT<R>& pa, cudaStream_t stream) {
+    const int ctas = (a.n_cars + TB2_PERSIST_BLOCK - 1) / TB2_PERSIST_BLOCK > 0 ? (a.n_cars + TB2_PERSIST_BLOCK - 1) / TB2_PERSIST_BLOCK : 1;
+    const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
+    void (*kern)(const StepArgsT<R>, const PersistArgsT<R>) = ens ? persistent_kernel<R, true> : persistent_kernel<R, false>;
+    if (ctas > 8) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas, 1, 1);
+    cfg.blockDim = dim3(TB2_PERSIST_BLOCK, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a, pa);
 }
 
 template <typename R>
