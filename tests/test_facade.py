@@ -119,3 +119,22 @@ def test_facade_accepts_foreign_lights_dataframe():
     st = cars_obj.state
     assert np.allclose(st["x"].to_numpy(float), g["x"][59], rtol=1e-12, atol=0)
     assert np.array_equal(start_len - np.array([len(p) for p in st["xpath"]]), g["cursor"][59])
+
+
+@pytest.mark.gpu
+def test_write_state_parquet_roundtrip(tmp_path):
+    """Cars(serialize=True) dumps the state every update like cars.py:43-58 (pyarrow instead of the absent fastparquet)."""
+    import pandas as pd
+    from traffic_b200.facade import Cars, TrafficLights
+    g = util.load_golden("c1_dt0.001_p2_s1")
+    cars_df, lights_df, graph = util.frames_from_golden(g)
+    cars_obj = Cars(cars_df, graph, serialize=True)
+    cars_obj.serialize_path = str(tmp_path / "data_store")
+    lights_obj = TrafficLights(lights_df, graph)
+    for _ in range(3):
+        lights_obj.update(1e-3)
+        cars_obj.update(1e-3, lights_obj.state)
+    files = sorted((tmp_path / "data_store").rglob("*.parquet.gz"))
+    assert len(files) == 3
+    back = pd.read_parquet(files[-1])
+    assert np.allclose(back["x"].to_numpy(float), g["x"][2], rtol=1e-12, atol=0) and len(back) == len(cars_df)
