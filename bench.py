@@ -295,14 +295,26 @@ def main():
     k = max(1, min(args.frame_every, args.steps))
     frames = max(1, args.steps // k)
     frame = torch.empty((N, 2), dtype=torch.float64 if prec == native.F64 else torch.float32).pin_memory()
+    # a FRESH simulation of the same world, warmed up by the same number of steps, so that the end-to-end leg advances
+    # through the same phase of the simulation as the device-resident leg (step cost drifts as queues build up)
+    stats_sim = sim
+    if ens is None:
+        del sim
+        sim = native.DeviceSim(w, precision=prec, write_aux=True,
+                               neighbor_mode=native.NEIGHBOR_SORT if args.neighbor == "sort" else native.NEIGHBOR_ATOMIC)
+        sim.step(dt, max(args.warmup - k, 0), order)
     go_in = torch.from_numpy(sim.download(native.FACE_GO).copy()).pin_memory()
     go_out = torch.empty_like(go_in).pin_memory()
-    sim.step_host(dt, k, order, go_in, frame, go_out)  # warm
+    frames_buf = [frame, torch.empty_like(frame).pin_memory()]   # double-buffered: frame f lands while f+1 is computed
+    sim.step_host_async(dt, min(k, max(args.warmup, 1)), order, go_in, frames_buf[0], go_out)  # warm
+    sim.frame_wait()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(frames):
-        go_in.copy_(go_out)
-        sim.step_host(dt, k, order, go_in, frame, go_out)
+    for f in range(frames):
+        go_in.copy_(go_out)                      # this interval's input: the light-face states, from pinned host memory
+        sim.step_host_async(dt, k, order, go_in, frames_buf[f & 1], go_out)
+        sim.frame_wait(faces_only=True)          # the next interval's input is on the host; the positions still travel
+    sim.frame_wait()                             # last position frame landed
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -313,9 +325,9 @@ def main():
     d2h = (frame.numel() * real_bytes + go_out.numel()) / k
 
     # ---- replica statistics gathered over NCCL (the only collective on this path) ----
-    rt = sim.tensor(native.ROUTE_TIME)
-    cur = sim.tensor(native.CURSOR)
-    end = sim.tensor(native.PATH_END)
+    rt = stats_sim.tensor(native.ROUTE_TIME)
+    cur = stats_sim.tensor(native.CURSOR)
+    end = stats_sim.tensor(native.PATH_END)
     stats = torch.stack([rt.mean(), (cur >= end).double().mean()]).to(torch.float32)
     if world > 1:
         allstats = torch.empty(world * 2, device="cuda", dtype=torch.float32)
@@ -326,7 +338,7 @@ def main():
     rollout = None
     if ens is not None:
         from traffic_b200 import ensemble
-        res = ensemble.gather_results(ens.results(sim.step_count), args.replicas)  # [R,4] trip_time, steps, done, id
+        res = ensemble.gather_results(ens.results(stats_sim.step_count), args.replicas)  # [R,4] trip_time, steps, done, id
         rollout = {"replicas": int(args.replicas), "arrived": int(np.nansum(res[:, 2])),
                    "mean_trip_time_arrived": float(np.nanmean(np.where(res[:, 2] > 0, res[:, 0], np.nan)))
                    if np.nansum(res[:, 2]) > 0 else None}

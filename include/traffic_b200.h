@@ -146,6 +146,16 @@ int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stre
 int tb2_step_host(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
                   void* frame_xy_out, uint8_t* face_go_out, void* stream);
 
+/* Pipelined frame extraction (animate.py-style consumers): like tb2_step_host but returns once the work
+ * is enqueued; the frame is snapshotted on the device and travels on a private copy stream while the caller enqueues the
+ * next batch.  Host buffers should be pinned.  The face states are copied first: tb2_frame_wait(sim, 1) returns when they
+ * have landed (microseconds), tb2_frame_wait(sim, 0) when the position frame has landed too.  A new tb2_step_host_async
+ * may be issued before the positions have landed (it orders itself after the pending copy); use a second position buffer
+ * for it. */
+int tb2_step_host_async(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
+                        void* frame_xy_out, uint8_t* face_go_out, void* stream);
+int tb2_frame_wait(tb2_sim* sim, int32_t faces_only);
+
 /* Init-time routing (the producer of the hot path's inputs): for every (origin, destination) pair the
  * shortest path by edge weight, i.e. networkx.shortest_path(G, o, d, weight='length') as navigation.get_route /
  * get_init_path / lines_to_node call it once per car and per light face (navigation.py:581-609, 764-841).  The graph is

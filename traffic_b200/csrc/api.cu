@@ -41,7 +41,7 @@ enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
     B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
     B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV,
-    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_LIGHTS, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
+    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_LIGHTS, B_FRAME_STAGE, B_GO_STAGE, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
     B_SORT_VALS_OUT, B_SORT_TEMP, B_COUNT
 };
 
@@ -108,6 +108,8 @@ Layout make_layout(const tb2_config& c) {
     b[B_DONE] = b[B_TRIP_STEP] = Rep * 4;
     b[B_TRIP_TIME] = Rep * 8;
     b[B_CELL_LIGHTS] = C * 32;
+    b[B_FRAME_STAGE] = N * 2 * R;   // snapshot of the positions / faces that a pipelined frame copy reads from
+    b[B_GO_STAGE] = Rep * F;
     const bool sorted = c.neighbor_mode == TB2_NEIGHBOR_SORT;
     b[B_SORT_KEYS_IN] = b[B_SORT_VALS_IN] = b[B_SORT_KEYS_OUT] = b[B_SORT_VALS_OUT] = sorted ? N * 4 : 0;
     b[B_SORT_TEMP] = sorted ? neighbor_sort_temp_bytes((int)N, key_bits_of(c)) : 0;
@@ -134,6 +136,10 @@ struct tb2_sim {
     bool allow_persistent = true;   // TB2_NO_PERSISTENT=1 in the environment forces one launch per step (A/B testing)
     int64_t launches = 0, steps = 0;
     double log_free_over_stop = 0.0;
+    // pipelined frame extraction (tb2_step_host_async): a private copy stream and two events
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t frame_ready = nullptr, frame_done = nullptr, faces_done = nullptr;
+    bool frame_pending = false;
 
     template <typename T>
     T* buf(int b) const { return reinterpret_cast<T*>(arena + lay.off[b]); }
@@ -341,6 +347,11 @@ int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_s
 
 int tb2_destroy(tb2_sim* s) {
     if (!s) return TB2_OK;
+    if (s->frame_pending) cudaEventSynchronize(s->frame_done);
+    if (s->frame_ready) cudaEventDestroy(s->frame_ready);
+    if (s->frame_done) cudaEventDestroy(s->frame_done);
+    if (s->faces_done) cudaEventDestroy(s->faces_done);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->owns_arena && s->arena) cudaFree(s->arena);
     delete s;
     return TB2_OK;
@@ -471,6 +482,53 @@ int tb2_step_host(tb2_sim* s, double dt, int32_t n_steps, int32_t order, const u
     if (frame_xy_out) if (int rc = tb2_download(s, TB2_POS, frame_xy_out, N * 2 * s->real_bytes(), stream)) return rc;
     if (face_go_out) if (int rc = tb2_download(s, TB2_FACE_GO, face_go_out, F, stream)) return rc;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return TB2_OK;
+}
+
+// Pipelined variant: returns as soon as the work is enqueued.  The positions / face states after the n_steps are
+// snapshotted on the device and copied to the host buffers on a private copy stream, so the caller can enqueue the next
+// batch of steps while the frame is in flight; tb2_frame_wait() blocks until the LAST requested frame has landed.
+int tb2_step_host_async(tb2_sim* s, double dt, int32_t n_steps, int32_t order, const uint8_t* face_go_in,
+                        void* frame_xy_out, uint8_t* face_go_out, void* stream_) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t F = (size_t)s->cfg.n_faces * s->cfg.n_replicas, N = (size_t)s->cfg.n_cars * s->cfg.n_replicas;
+    if (!s->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->frame_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->frame_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->faces_done, cudaEventDisableTiming));
+    }
+    if (face_go_in) if (int rc = tb2_upload(s, TB2_FACE_GO, face_go_in, F, stream)) return rc;
+    if (int rc = tb2_step(s, dt, n_steps, order, stream)) return rc;
+    if (frame_xy_out || face_go_out) {
+        // the staging buffers may still be read by the previous frame's host copy
+        if (s->frame_pending) CU(cudaStreamWaitEvent(stream, s->frame_done, 0));
+        if (frame_xy_out) CU(cudaMemcpyAsync(s->buf<char>(B_FRAME_STAGE), tb2_field_ptr(s, TB2_POS), N * 2 * s->real_bytes(),
+                                             cudaMemcpyDeviceToDevice, stream));
+        if (face_go_out && F) CU(cudaMemcpyAsync(s->buf<char>(B_GO_STAGE), tb2_field_ptr(s, TB2_FACE_GO), F,
+                                                 cudaMemcpyDeviceToDevice, stream));
+        CU(cudaEventRecord(s->frame_ready, stream));
+        CU(cudaStreamWaitEvent(s->copy_stream, s->frame_ready, 0));
+        // the (small) face states go first so that a caller that feeds them back as the next input waits microseconds
+        if (face_go_out && F) CU(cudaMemcpyAsync(face_go_out, s->buf<char>(B_GO_STAGE), F, cudaMemcpyDeviceToHost,
+                                                 s->copy_stream));
+        CU(cudaEventRecord(s->faces_done, s->copy_stream));
+        if (frame_xy_out) CU(cudaMemcpyAsync(frame_xy_out, s->buf<char>(B_FRAME_STAGE), N * 2 * s->real_bytes(),
+                                             cudaMemcpyDeviceToHost, s->copy_stream));
+        CU(cudaEventRecord(s->frame_done, s->copy_stream));
+        s->frame_pending = true;
+    }
+    return TB2_OK;
+}
+
+int tb2_frame_wait(tb2_sim* s, int32_t faces_only) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    if (s->frame_pending) {
+        if (faces_only) { CU(cudaEventSynchronize(s->faces_done)); return TB2_OK; }
+        CU(cudaEventSynchronize(s->frame_done));
+        s->frame_pending = false;
+    }
     return TB2_OK;
 }
 

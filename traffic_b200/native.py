@@ -33,7 +33,8 @@ FIELD_COUNT = 24
 
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
            "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
-           "tb2_launch_count", "tb2_step_count", "tb2_route_paths", "tb2_route_last_error"]
+           "tb2_launch_count", "tb2_step_count", "tb2_route_paths", "tb2_route_last_error", "tb2_step_host_async",
+           "tb2_frame_wait"]
 
 
 class Tb2Config(C.Structure):
@@ -89,6 +90,8 @@ def lib():
         L.tb2_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
         L.tb2_step_host.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
+        L.tb2_step_host_async.argtypes = L.tb2_step_host.argtypes
+        L.tb2_frame_wait.argtypes = [C.c_void_p, C.c_int32]
         L.tb2_cars_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.tb2_lights_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.tb2_route_paths.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
@@ -256,6 +259,17 @@ class DeviceSim:
         with self._torch.cuda.device(self.device):
             _check(self.L.tb2_step_host(self.h, C.c_double(dt), C.c_int32(n_steps), C.c_int32(order), p(face_go_in),
                                         p(frame_out), p(face_go_out), self._stream()), "tb2_step_host")
+
+    def step_host_async(self, dt, n_steps, order, face_go_in=None, frame_out=None, face_go_out=None):
+        """Pipelined ``step_host``: returns once enqueued; ``frame_wait()`` blocks until the last frame has landed."""
+        def p(a):
+            return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        with self._torch.cuda.device(self.device):
+            _check(self.L.tb2_step_host_async(self.h, C.c_double(dt), C.c_int32(n_steps), C.c_int32(order), p(face_go_in),
+                                              p(frame_out), p(face_go_out), self._stream()), "tb2_step_host_async")
+
+    def frame_wait(self, faces_only: bool = False):
+        _check(self.L.tb2_frame_wait(self.h, 1 if faces_only else 0), "tb2_frame_wait")
 
     def download_world(self, w: World, replica: int = 0) -> World:
         """Refresh the mutable fields of ``w`` from the device (of one replica when this is an ensemble)."""
