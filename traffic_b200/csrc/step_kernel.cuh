@@ -78,7 +78,7 @@ __device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, 
 // to b in double mode; b + origin in float mode where coordinates are stored relative to the map origin).
 template <typename R>
 __device__ __forceinline__ bool isclose_abs(R a, R b, R b_abs, R rtol, R atol) {
-    return ((fabs(a - b) <= atol + rtol * fabs(b_abs)) && isfinite(b)) || (a == b);
+    return ((fabs(a - b) <= atol + rtol * fabs(b_abs)) & (bool)isfinite(b)) | (a == b);   // no short-circuit: branch-free
 }
 template <typename R>
 __device__ __forceinline__ bool isclose_(R a, R b, R rtol, R atol) { return isclose_abs<R>(a, b, b, rtol, atol); }
@@ -334,7 +334,7 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     const bool has_path = cur < eff;
     const int path_len = has_path ? end - cur : 0;
     // FrontView.crossed_node_event (navigation.py:91-111): tolerance relative to the car's ABSOLUTE coordinate
-    const bool crossed = has_path && isclose_abs<R>(head.x, x, x + a.origin_x, R(1.0e-5), R(1.0e-8)) &&
+    const bool crossed = has_path & isclose_abs<R>(head.x, x, x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
                          isclose_abs<R>(head.y, y, y + a.origin_y, R(1.0e-5), R(1.0e-8));
     R2 t = head;
     if (!has_path || (crossed && path_len < 2)) t = a.dest_xy[i];
@@ -406,7 +406,7 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
         f = fabs(f);
         vx = dx / d_node * a.speed_limit * f;
         vy = dy / d_node * a.speed_limit * f;
-        if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) && isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
+        if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) & isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
             const bool acc = !r_t && (!c_t || d_car > a.stop_distance);
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
         }
