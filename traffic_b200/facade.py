@@ -146,6 +146,7 @@ class Cars:
         self._sim = None
         self._world = None
         self._lights_owner = None
+        self._foreign = None      # the caller's own lights DataFrame when it is not one of our TrafficLights
         self._updates = 0
 
     @property
@@ -163,8 +164,7 @@ class Cars:
         w = world_from_dataframes(cars_df, lights_df, self.graph, params=_reference_params())
         if owner is not None:
             w.lights_time = float(owner.time_elapsed)
-        if self._world is not None:  # re-bind: keep route cursors (frame xpath is already the remaining path)
-            pass
+        # (on a re-bind mid-run the frame's xpath/ypath already hold only the remaining route, so cursors carry over)
         if self._sim is not None:
             self._sim.close()
         self._sim = native.DeviceSim(w)
