@@ -316,3 +316,29 @@ def test_pipelined_frame_extraction_equals_synchronous():
         assert torch.equal(a, b)
     for a, b in zip(sync_go, got_go):
         assert torch.equal(a, b)
+
+
+def test_routes_with_zero_coordinates_follow_the_any_rule():
+    """`np.array(xpath).any() and np.array(ypath).any()` (navigation.py:37-39): a route whose remaining points have an
+    all-zero x or y column counts as exhausted even though points are left (path_eff_end < path_end)."""
+    native = _native()
+    from oracle import oracle
+    from traffic_b200.state import make_world
+    X, Y = 566000.0, 4186000.0
+    axis = (X - 100.0, X + 900.0, Y - 100.0, Y + 900.0)
+    pos = np.array([[X + 10.0, Y + 12.0], [X + 300.0, Y + 310.0], [X + 500.0, Y + 40.0]])
+    paths = [np.array([[X + 32.0, Y + 30.5], [X + 70.0, 0.0], [X + 90.0, 0.0]]),   # y is all-zero after the first point
+             np.array([[X + 325.0, Y + 340.0], [0.0, Y + 400.0]]),                # x is all-zero after the first point
+             np.array([[X + 520.0, Y + 70.0], [X + 560.0, Y + 95.0]])]
+    dest = np.array([[X + 80.0, Y + 5.0], [X + 5.0, Y + 400.0], [X + 560.0, Y + 95.0]])
+    ptr = np.concatenate([[0], np.cumsum([len(p) for p in paths])])
+    w = make_world(axis, pos, ptr, np.concatenate(paths), dest)
+    assert w.path_eff_end[0] < w.path_end[0] and w.path_eff_end[1] < w.path_end[1]
+    wg, wc = w.copy(), w.copy()
+    sim = native.DeviceSim(wg)
+    for s in range(60):
+        sim.step(1e-3, 2, 1)
+        oracle.run(wc, 1e-3, 2, 1)
+        sim.download_world(wg)
+        _compare_worlds(wg, wc, FLOAT_RTOL, "step %d" % (2 * s + 2))
+    assert wc.cursor[1] == wc.path_end[1] and (wc.vel[1] == 0).all(), "car 1 should have run out of usable route"

@@ -385,6 +385,7 @@ int tb2_upload(tb2_sim* s, int field, const void* src, size_t bytes, void* strea
     if (bytes && !src) return fail(TB2_ERR_INVALID, "null source");
     if (bytes) CU(cudaMemcpyAsync(s->arena + s->lay.off[b], src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     if (field == TB2_POS || field == TB2_CURSOR || field == TB2_PATH_END || field == TB2_PATH_XY ||
+        field == TB2_PATH_EFF_END || field == TB2_DEST_XY ||
         field == TB2_FACE_VEC || field == TB2_LIGHT_XY || field == TB2_FACE_PTR || field == TB2_CELL_LIGHT_PTR ||
         field == TB2_CELL_LIGHT_IDX) s->prepared = false;
     return TB2_OK;

@@ -336,9 +336,11 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     // FrontView.crossed_node_event (navigation.py:91-111): tolerance relative to the car's ABSOLUTE coordinate
     const bool crossed = has_path & isclose_abs<R>(head.x, x, x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
                          isclose_abs<R>(head.y, y, y + a.origin_y, R(1.0e-5), R(1.0e-8));
+    // target (FrontView.upcoming_node_position, navigation.py:73-89).  head_xy holds the destination once the route is
+    // exhausted (written below / by prepare), so a parked car needs no extra load; only the step that crosses the last
+    // route point fetches dest_xy, and a crossing step fetches the next route point.
     R2 t = head;
-    if (!has_path || (crossed && path_len < 2)) t = a.dest_xy[i];
-    else if (crossed) t = a.path_xy[cur + 1];
+    if (crossed) t = (path_len < 2) ? a.dest_xy[i] : a.path_xy[cur + 1];
 
     const R dx = t.x - x, dy = t.y - y;
     const R d_node = norm2<R>(dx, dy);
@@ -412,10 +414,9 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
         }
         if (crossed) {
             a.cursor[i] = cur + 1;
-            if (cur + 1 < end) {          // new head: the point we just steered to
-                a.head_xy[i] = t;
-                a.head_curv[i] = a.pt_curv[cur + 1];
-            }
+            // new head: the point we just steered to, or the destination once no usable route point is left
+            a.head_xy[i] = (cur + 1 >= eff && path_len >= 2) ? a.dest_xy[i] : t;
+            if (cur + 1 < end) a.head_curv[i] = a.pt_curv[cur + 1];
         }
     } else if (cur != end) {
         a.cursor[i] = end;  // path becomes []
@@ -522,7 +523,8 @@ template <typename R>
 __global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgsT<R> g,
                                                            const typename real2<R>::type* __restrict__ pos,
                                                            const int32_t* __restrict__ cursor,
-                                                           const int32_t* __restrict__ path_end,
+                                                           const int32_t* __restrict__ path_eff_end,
+                                                           const typename real2<R>::type* __restrict__ dest_xy,
                                                            const typename real2<R>::type* __restrict__ path_xy,
                                                            const typename real2<R>::type* __restrict__ pt_curv,
                                                            typename real2<R>::type* head_xy,
@@ -531,8 +533,9 @@ __global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgsT
     const int i = (int)blockIdx.x * 256 + (int)threadIdx.x;
     if (i >= n_cars) return;
     const int cur = cursor[i];
-    typename real2<R>::type h = mk2(R(0), R(0)), hc = h;
-    if (cur < path_end[i]) { h = path_xy[cur]; hc = pt_curv[cur]; }
+    // head cache: the current route point while the car has a route (navigation.py:37-39 rule), else the destination
+    typename real2<R>::type h = dest_xy[i], hc = mk2(R(0), R(0));
+    if (cur < path_eff_end[i]) { h = path_xy[cur]; hc = pt_curv[cur]; }
     head_xy[i] = h;
     head_curv[i] = hc;
     const typename real2<R>::type p = pos[i];
@@ -628,7 +631,7 @@ void launch_prepare_t(const StepArgsT<R>& a, typename real2<R>::type* pt_curv, t
         prepare_points_kernel<R><<<(a.n_cars + 127) / 128, 128, 0, stream>>>(a.n_cars, a.cursor, a.path_end, a.path_xy,
                                                                                pt_curv, a.stop_distance, a.free_distance);
         prepare_cars_kernel<R><<<(a.n_cars + 255) / 256, 256, 0, stream>>>(
-            a.n_cars, a.g, a.pos_in, a.cursor, a.path_end, a.path_xy, pt_curv, a.head_xy, a.head_curv, a.cell,
+            a.n_cars, a.g, a.pos_in, a.cursor, a.path_eff_end, a.dest_xy, a.path_xy, pt_curv, a.head_xy, a.head_curv, a.cell,
             a.cell_prev, tab3 + (size_t)2 * a.g.n_cells * a.n_replicas * cur_table, a.cars_per_replica);
     }
 }
