@@ -5,7 +5,7 @@
  * legs may load it.  The product path (traffic_b200/csrc) never calls into it.
  *
  * Parity status: PINNED - tests/test_oracle_golden.py checks this restatement against per-step vectors recorded
- * from the unmodified reference (oracle/ref_harness.py -> tests/golden/*.npz): discrete outputs bit-exact,
+ * from the unmodified reference (oracle/ref_harness.py -> tests/golden/ (npz files)): discrete outputs bit-exact,
  * floats to <= a few ulp (np.arccos is an SVML vector routine in the numpy build that made the fixtures, libm
  * acos here).
  *
