@@ -451,10 +451,16 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
     if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (state was uploaded since)");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (s->allow_persistent && n_steps >= 2 && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC &&
-        (int64_t)s->cfg.n_cars * s->cfg.n_replicas <= persistent_max_cars()) {
+        (int64_t)s->cfg.n_cars * s->cfg.n_replicas <= persistent_max_cars(s->cfg.precision == TB2_F32)) {
         // small world: the whole batch is one launch of the persistent cluster kernel
-        CU(s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, n_steps, order, stream)
-                                       : step_persistent_t<float>(s, dt, n_steps, order, stream));
+        const cudaError_t pe = s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, n_steps, order, stream)
+                                                           : step_persistent_t<float>(s, dt, n_steps, order, stream);
+        if (pe == cudaErrorCooperativeLaunchTooLarge) {   // the device is shared: fall back to one launch per step for good
+            (void)cudaGetLastError();
+            s->allow_persistent = false;
+            return tb2_step(s, dt, n_steps, order, stream_);
+        }
+        CU(pe);
         s->launches++;
         s->cur_pos ^= (n_steps & 1);
         s->cur_tab = (s->cur_tab + n_steps) % 3;

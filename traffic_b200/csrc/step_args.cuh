@@ -106,7 +106,8 @@ using StepArgs32 = StepArgsT<float>;
 int step_block_threads();
 void launch_step(const StepArgs64& a, cudaStream_t stream);
 void launch_step(const StepArgs32& a, cudaStream_t stream);
-int persistent_max_cars();
+int persistent_max_cars(int precision_f32);   // largest world the persistent (one launch per batch) kernels can take
+int persistent_grid_capacity_f32();
 cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream);
 cudaError_t launch_persistent(const StepArgs32& a, const PersistArgsT<float>& pa, cudaStream_t stream);
 // (re)derive everything the step kernel keeps cached from the uploaded state: per-point curvature constants, per-car

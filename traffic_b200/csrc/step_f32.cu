@@ -4,6 +4,8 @@
 
 void launch_step(const StepArgs32& a, cudaStream_t stream) { tb2k::launch_step_t<float>(a, stream); }
 
+int persistent_grid_capacity_f32() { return tb2k::persistent_grid_capacity_t<float>(); }
+
 cudaError_t launch_persistent(const StepArgs32& a, const PersistArgsT<float>& pa, cudaStream_t stream) {
     return tb2k::launch_persistent_t<float>(a, pa, stream);
 }

@@ -17,7 +17,13 @@ int step_block_threads() { return TB2_BLOCK; }
 
 void launch_step(const StepArgs64& a, cudaStream_t stream) { tb2k::launch_step_t<double>(a, stream); }
 
-int persistent_max_cars() { return TB2_PERSIST_BLOCK * TB2_PERSIST_MAX_CTAS; }
+int persistent_max_cars(int precision_f32) {
+    static int cap64 = -1, cap32 = -1;   // the cooperative variant's capacity depends on the device: query once
+    const int cluster_cap = TB2_PERSIST_BLOCK * TB2_PERSIST_MAX_CTAS;
+    int& cap = precision_f32 ? cap32 : cap64;
+    if (cap < 0) cap = precision_f32 ? persistent_grid_capacity_f32() : tb2k::persistent_grid_capacity_t<double>();
+    return cap > cluster_cap ? cap : cluster_cap;
+}
 cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream) {
     return tb2k::launch_persistent_t<double>(a, pa, stream);
 }

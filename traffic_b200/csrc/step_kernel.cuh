@@ -468,11 +468,18 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
 // and meet at a hardware cluster barrier (release/acquire, so the positions, table entries and face states written in
 // step s are visible to every CTA in step s+1) instead of returning to the host between steps - at 2k cars a step is a
 // single wave of warps and the per-launch gap is a third of the step time.
-template <typename R, bool ENS>
-__global__ void __launch_bounds__(TB2_PERSIST_BLOCK, 1) persistent_kernel(const __grid_constant__ StepArgsT<R> a,
-                                                                          const __grid_constant__ PersistArgsT<R> pa) {
+// GRID = false: the CTAs are one thread-block cluster and meet at the hardware cluster barrier (<= 16 CTAs).
+// GRID = true : cooperative launch, every CTA co-resident, grid-wide barrier (mid-size worlds, one wave of CTAs).
+template <bool GRID>
+__device__ __forceinline__ void step_barrier() {
     namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
+    if constexpr (GRID) cg::this_grid().sync();
+    else cg::this_cluster().sync();
+}
+
+template <typename R, bool ENS, bool GRID>
+__global__ void __launch_bounds__(TB2_PERSIST_BLOCK, GRID ? 2 : 1)
+persistent_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ PersistArgsT<R> pa) {
     const int nthreads = (int)(gridDim.x * blockDim.x);
     const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int n_tab = 2 * a.g.n_cells * a.n_replicas;
@@ -483,7 +490,7 @@ __global__ void __launch_bounds__(TB2_PERSIST_BLOCK, 1) persistent_kernel(const 
             lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
                              pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1]);
         cgo ^= 1; ck ^= 1;
-        cluster.sync();
+        step_barrier<GRID>();
     }
     for (int s = 0; s < pa.n_steps; ++s) {
         const bool tick = pa.order != TB2K_ORDER_LIGHTS_CARS || s < pa.n_steps - 1;
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(TB2_PERSIST_BLOCK, 1) persistent_kernel(const 
             cgo ^= 1; ck ^= 1;
         }
         cp ^= 1; ct = (ct + 1) % 3;
-        cluster.sync();
+        step_barrier<GRID>();
     }
 }
 
@@ -596,11 +603,32 @@ void launch_step_t(const StepArgsT<R>& a, cudaStream_t stream) {
     }
 }
 
+// How many cars the cooperative (grid-barrier) variant can take on this device: every CTA must be co-resident.
+template <typename R>
+int persistent_grid_capacity_t() {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel<R, false, true>, TB2_PERSIST_BLOCK, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return sms * per_sm * TB2_PERSIST_BLOCK;
+}
+
 template <typename R>
 cudaError_t launch_persistent_t(const StepArgsT<R>& a, const PersistArgsT<R>& pa, cudaStream_t stream) {
-    const int ctas = (a.n_cars + TB2_PERSIST_BLOCK - 1) / TB2_PERSIST_BLOCK > 0 ? (a.n_cars + TB2_PERSIST_BLOCK - 1) / TB2_PERSIST_BLOCK : 1;
+    int ctas = (a.n_cars + TB2_PERSIST_BLOCK - 1) / TB2_PERSIST_BLOCK;
+    if (ctas < 1) ctas = 1;
     const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
-    void (*kern)(const StepArgsT<R>, const PersistArgsT<R>) = ens ? persistent_kernel<R, true> : persistent_kernel<R, false>;
+    if (ctas > TB2_PERSIST_MAX_CTAS) {   // mid-size world: cooperative launch + grid barrier
+        void (*kern)(const StepArgsT<R>, const PersistArgsT<R>) =
+            ens ? persistent_kernel<R, true, true> : persistent_kernel<R, false, true>;
+        void* args[2] = {(void*)&a, (void*)&pa};
+        return cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas, 1, 1), dim3(TB2_PERSIST_BLOCK, 1, 1), args, 0, stream);
+    }
+    void (*kern)(const StepArgsT<R>, const PersistArgsT<R>) =
+        ens ? persistent_kernel<R, true, false> : persistent_kernel<R, false, false>;
     if (ctas > 8) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
