@@ -218,25 +218,26 @@ class Cars:
         f["vx"], f["vy"] = w.vel[:, 0], w.vel[:, 1]
         f["route-time"] = w.route_time
         f["distance-to-node"] = w.d_node
-        dc = np.empty(n, object)
-        dl = np.empty(n, object)
-        for i in range(n):
-            v = w.d_car[i]
-            dc[i] = float(v) if v != 0.0 else False
-            v = w.d_light[i]
-            dl[i] = float(v) if v != 0.0 else (None if np.signbit(v) else False)
+        # mixed-type columns of the reference (Appendix B-4): a distance, False, or (lights only) None
+        dc = w.d_car.astype(object)
+        dc[w.d_car == 0.0] = False
+        dl = w.d_light.astype(object)
+        zero = w.d_light == 0.0
+        dl[zero & ~np.signbit(w.d_light)] = False
+        dl[zero & np.signbit(w.d_light)] = None
         f["distance-to-car"] = dc
         f["distance-to-red-light"] = dl
         ncx = w.grid.ncx
         f["xbin"] = (w.cell % ncx).astype(np.int64)
         f["ybin"] = (w.cell // ncx).astype(np.int64)
-        px, py = w.path_xy[:, 0], w.path_xy[:, 1]
+        # remaining route of every car as Python lists (the reference pops the head of these lists, simulation.py:47-52)
+        px, py = w.path_xy[:, 0].tolist(), w.path_xy[:, 1].tolist()
+        cur, end = w.cursor.tolist(), w.path_end.tolist()
         xs = np.empty(n, object)
         ys = np.empty(n, object)
-        for i in range(n):
-            a, b = int(w.cursor[i]), int(w.path_end[i])
-            xs[i] = px[a:b].tolist()
-            ys[i] = py[a:b].tolist()
+        for i, (a, b) in enumerate(zip(cur, end)):   # element-wise: numpy would broadcast equal-length lists to 2-D
+            xs[i] = px[a:b]
+            ys[i] = py[a:b]
         f["xpath"], f["ypath"] = xs, ys
         if self._updates > 0 and "route" in f.columns:
             f["route"] = np.nan  # the reference wipes this column on the first update (simulation.py:30,76; B-7)
