@@ -55,3 +55,25 @@ def test_init_then_facade_loop_matches_golden_end_to_end():
     assert np.allclose(st["y"].to_numpy(float), g["y"][199], rtol=1e-12, atol=0)
     go = np.concatenate([np.asarray(v).astype(np.uint8) for v in lights.state["go-values"]])
     assert np.array_equal(go, g["face_go"][199])
+
+
+def test_init_on_a_plain_networkx_graph_equals_array_path():
+    """An OGraph-like object that only has `.G` (networkx MultiDiGraph) and `.axis` - what the reference's callers pass -
+    must give the same frames as the SynthGraph fast path."""
+    from types import SimpleNamespace
+    from traffic_b200 import init, synth
+
+    graph = synth.SynthGraph(12, 12, seed=3)
+    plain = SimpleNamespace(G=graph.G, axis=graph.axis)
+    random.seed(7)
+    c1 = init.init_random_node_start_location(60, graph)
+    l1 = init.init_traffic_lights(graph, prescale=3)
+    random.seed(7)
+    c2 = init.init_random_node_start_location(60, plain)
+    l2 = init.init_traffic_lights(plain, prescale=3)
+    for col in ("x", "y", "origin", "destination", "xbin", "ybin"):
+        assert np.array_equal(c1[col].to_numpy(), c2[col].to_numpy()), col
+    assert all(a == b for a, b in zip(c1["xpath"], c2["xpath"])) and all(a == b for a, b in zip(c1["route"], c2["route"]))
+    for col in ("node", "degree", "x", "y", "switch-time", "xbin", "ybin"):
+        assert np.array_equal(l1[col].to_numpy(), l2[col].to_numpy()), col
+    assert all(a == b for a, b in zip(l1["out-xvectors"], l2["out-xvectors"]))

@@ -87,3 +87,20 @@ def test_routing_limit_and_errors():
     assert pl[0] == 2 and pl[1] == -1          # the far corner is outside the search radius
     with pytest.raises(native.NativeError):
         routing.shortest_paths(indptr, indices, w, [0], [400])
+
+
+def test_polylines_with_edge_geometry():
+    """OSMnx edges may carry a `geometry` polyline (navigation.py:823-827): it replaces the straight segment, and
+    consecutive duplicates (the shared node between two edges) are dropped like models.path_decompiler does."""
+    node_xy = np.array([[0.0, 0.0], [10.0, 0.0], [10.0, 10.0]])
+    geom = {(0, 1): np.array([[0.0, 0.0], [4.0, 1.0], [7.0, 1.0], [10.0, 0.0]])}      # edge 1->2 has no geometry
+    path_len = np.array([3, 2, 1], np.int32)
+    path_nodes = np.array([[0, 1, 2], [1, 2, 0], [2, 0, 0]], np.int32)
+    ptr, xy = routing.polylines_with_geometry(node_xy, path_len, path_nodes, geom)
+    assert ptr.tolist() == [0, 5, 7, 7]
+    assert xy[:5].tolist() == [[0.0, 0.0], [4.0, 1.0], [7.0, 1.0], [10.0, 0.0], [10.0, 10.0]]
+    assert xy[5:7].tolist() == [[10.0, 0.0], [10.0, 10.0]]
+    # without geometry it must agree with the vectorised version
+    ptr2, xy2 = routing.polylines_with_geometry(node_xy, path_len, path_nodes, {})
+    ptr3, xy3 = routing.polylines(node_xy, path_len, path_nodes)
+    assert np.array_equal(ptr2, ptr3) and np.array_equal(xy2, xy3)

@@ -24,15 +24,25 @@ def _graph_arrays(graph):
     with node ``x``/``y`` and edge ``length``) or a ``SynthGraph`` (arrays already there)."""
     if hasattr(graph, "node_xy") and hasattr(graph, "edge_u"):
         ids = np.asarray(graph.node_ids)
-        return ids, np.asarray(graph.node_xy, np.float64), routing.csr_of(graph.n_nodes, graph.edge_u, graph.edge_v, graph.edge_len), None
+        return ids, np.asarray(graph.node_xy, np.float64), routing.csr_of(graph.n_nodes, graph.edge_u, graph.edge_v, graph.edge_len), None, {}
     G = graph.G
     ids = np.asarray(list(G.nodes()))
     index = {nid: i for i, nid in enumerate(ids.tolist())}
     xy = np.asarray([[G.nodes[n]["x"], G.nodes[n]["y"]] for n in ids.tolist()], np.float64)
     eu, ev, el = [], [], []
+    best, geom = {}, {}
     for u, v, data in G.edges(data=True):
-        eu.append(index[u]); ev.append(index[v]); el.append(float(data["length"]))
-    return ids, xy, routing.csr_of(len(ids), eu, ev, el), G
+        a, b, ln = index[u], index[v], float(data["length"])
+        eu.append(a); ev.append(b); el.append(ln)
+        # the shortest of parallel edges supplies the line geometry (navigation.py:820-827)
+        if (a, b) not in best or ln < best[(a, b)]:
+            best[(a, b)] = ln
+            if "geometry" in data:
+                gx, gy = data["geometry"].xy
+                geom[(a, b)] = np.stack([np.asarray(gx, np.float64), np.asarray(gy, np.float64)], 1)
+            else:
+                geom.pop((a, b), None)
+    return ids, xy, routing.csr_of(len(ids), eu, ev, el), G, geom
 
 
 def _adjacency_order(graph, ids):
@@ -50,7 +60,7 @@ def _adjacency_order(graph, ids):
 def init_random_node_start_location(n, graph, car_id=None, alternate_route=None):
     import pandas as pd
 
-    ids, xy, (indptr, indices, w), _ = _graph_arrays(graph)
+    ids, xy, (indptr, indices, w), _, geom = _graph_arrays(graph)
     nodes = np.arange(len(ids))[:n]                      # nav.find_nodes: the first n nodes
     origins, dests = [], []
     for i in range(n):
@@ -60,7 +70,8 @@ def init_random_node_start_location(n, graph, car_id=None, alternate_route=None)
             dests.append(nodes[random_index] if random_index != n else nodes[0])
     origins, dests = np.asarray(origins, np.int32), np.asarray(dests, np.int32)
     path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origins, dests)
-    ptr, pxy = routing.polylines(xy, path_len, path_nodes)
+    ptr, pxy = (routing.polylines_with_geometry(xy, path_len, path_nodes, geom) if geom
+                else routing.polylines(xy, path_len, path_nodes))
     cars_data = []
     for k in range(len(origins)):
         if path_len[k] < 0:                              # NetworkXNoPath: the reference skips the car
@@ -86,7 +97,7 @@ def init_traffic_lights(graph, prescale=10):
     import pandas as pd
 
     epsilon = 0.3                                         # simulation.py:337
-    ids, xy, (indptr, indices, w), G = _graph_arrays(graph)
+    ids, xy, (indptr, indices, w), G, geom = _graph_arrays(graph)
     adj = _adjacency_order(graph, ids)
     if G is not None:
         degree = [d for _, d in G.degree()]
@@ -103,7 +114,9 @@ def init_traffic_lights(graph, prescale=10):
         for _ in adj[i]:
             if path_len[k] >= 2:
                 first_hop = path_nodes[k, 1]
-                vectors.append((xy[first_hop, 0] - xy[i, 0], xy[first_hop, 1] - xy[i, 1]))
+                g = geom.get((int(path_nodes[k, 0]), int(first_hop)))
+                second = g[1] if g is not None and len(g) > 1 else xy[first_hop]   # lines_to_node(...)[0][1]
+                vectors.append((second[0] - xy[i, 0], second[1] - xy[i, 1]))
             k += 1
         out_vectors = np.array(vectors)
         deg = len(out_vectors)

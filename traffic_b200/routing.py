@@ -71,3 +71,33 @@ def polylines(node_xy, path_len, path_nodes):
     ptr = np.zeros(n + 1, np.int64)
     np.cumsum(kept_len, out=ptr[1:])
     return ptr, xy[keep]
+
+
+def polylines_with_geometry(node_xy, path_len, path_nodes, edge_geom):
+    """Like ``polylines`` for graphs whose edges carry an OSMnx ``geometry`` (``navigation.py:823-827``): the polyline of
+    edge (u, v) replaces the straight segment.  ``edge_geom`` maps ``(u_index, v_index)`` to an ``(k, 2)`` array (the
+    geometry of the shortest parallel edge); edges without an entry contribute their two end points.  Consecutive
+    duplicates are dropped as ``models.path_decompiler`` does (an element survives iff it differs from its successor;
+    the last one always survives)."""
+    node_xy = np.asarray(node_xy, np.float64)
+    ptr = [0]
+    chunks = []
+    for k in range(len(path_len)):
+        n = int(path_len[k])
+        pts = []
+        for a, b in zip(path_nodes[k, :max(n, 0) - 1].tolist() if n >= 2 else [], path_nodes[k, 1:max(n, 0)].tolist() if n >= 2 else []):
+            g = edge_geom.get((a, b))
+            if g is None:
+                pts.append(node_xy[a]); pts.append(node_xy[b])
+            else:
+                pts.extend(np.asarray(g, np.float64).reshape(-1, 2))
+        if pts:
+            arr = np.asarray(pts, np.float64).reshape(-1, 2)
+            keep = np.ones(len(arr), bool)
+            keep[:-1] = (arr[:-1] != arr[1:]).any(1)
+            arr = arr[keep]
+        else:
+            arr = np.zeros((0, 2))
+        chunks.append(arr)
+        ptr.append(ptr[-1] + len(arr))
+    return np.asarray(ptr, np.int64), (np.concatenate(chunks) if chunks else np.zeros((0, 2))).reshape(-1, 2)
