@@ -39,9 +39,9 @@ size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 // internal buffer ids (superset of tb2_field: ping-pong partners, caches and the cell tables)
 enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
-    B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_TAB, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
+    B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_CELL_DYN, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
     B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV,
-    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_LIGHTS, B_FRAME_STAGE, B_GO_STAGE, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
+    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_STAT, B_LIGHT_CELLINFO, B_FRAME_STAGE, B_GO_STAGE, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
     B_SORT_VALS_OUT, B_SORT_TEMP, B_COUNT
 };
 
@@ -96,7 +96,7 @@ Layout make_layout(const tb2_config& c) {
     b[B_PT_CURV] = P * 2 * R;
     b[B_FACE_UNIT] = F * 2 * R;
     b[B_LEADER] = N * 4;
-    b[B_TAB] = 3 * 2 * C * Rep * 4;
+    b[B_CELL_DYN] = C * Rep * sizeof(CellDynT);   // three rotating (min, second) tables + two go words per bin
     b[B_LIGHT_XY] = L * 2 * R;
     b[B_SWITCH_TIME] = Rep * L * 8;
     b[B_FACE_PTR] = (L + 1) * 4;
@@ -107,7 +107,8 @@ Layout make_layout(const tb2_config& c) {
     b[B_T0] = b[B_T1] = 8;
     b[B_DONE] = b[B_TRIP_STEP] = Rep * 4;
     b[B_TRIP_TIME] = Rep * 8;
-    b[B_CELL_LIGHTS] = C * 32;
+    b[B_CELL_STAT] = C * 32;
+    b[B_LIGHT_CELLINFO] = L * 8;
     b[B_FRAME_STAGE] = N * 2 * R;   // snapshot of the positions / faces that a pipelined frame copy reads from
     b[B_GO_STAGE] = Rep * F;
     const bool sorted = c.neighbor_mode == TB2_NEIGHBOR_SORT;
@@ -133,6 +134,7 @@ struct tb2_sim {
     int n_cells = 0;
     int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
+    bool go_dirty = false;          // TB2_FACE_GO was uploaded: the per-bin go words must be re-derived before the next step
     bool allow_persistent = true;   // TB2_NO_PERSISTENT=1 in the environment forces one launch per step (A/B testing)
     int64_t launches = 0, steps = 0;
     double log_free_over_stop = 0.0;
@@ -225,7 +227,11 @@ void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
     a->face_unit = s->buf<R2>(B_FACE_UNIT);
     a->cell_light_ptr = s->buf<int32_t>(B_CELL_LIGHT_PTR);
     a->cell_light_idx = s->buf<int32_t>(B_CELL_LIGHT_IDX);
-    a->cell_lights = s->buf<CellLightsT<R>>(B_CELL_LIGHTS);
+    a->cell_stat = s->buf<CellStatT<R>>(B_CELL_STAT);
+    a->light_cellinfo = s->buf<int2>(B_LIGHT_CELLINFO);
+    a->cell_dyn = s->buf<CellDynT>(B_CELL_DYN);
+    a->tab_cur_k = s->cur_tab; a->tab_next_k = (s->cur_tab + 1) % 3; a->tab_clear_k = (s->cur_tab + 2) % 3;
+    a->go_k_cur = s->cur_go;
     a->switch_time = s->buf<double>(B_SWITCH_TIME);
     a->pos_in = s->buf<R2>(s->cur_pos ? B_POS1 : B_POS0);
     a->pos_out = s->buf<R2>(s->cur_pos ? B_POS0 : B_POS1);
@@ -241,40 +247,47 @@ void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
 // TrafficLights.update (cars.py:123-133) as its own launch
 void tick_lights(tb2_sim* s, double dt, cudaStream_t stream) {
     const tb2_config& c = s->cfg;
-    launch_lights_tick(c.n_replicas * c.n_lights, c.n_lights > 0 ? c.n_lights : 1, c.n_faces, dt,
+    // (a stale go word of the CURRENT buffer is harmless here: the tick reads the face bytes and writes the next word)
+    launch_lights_tick(c.n_replicas * c.n_lights, c.n_lights > 0 ? c.n_lights : 1, c.n_faces, s->n_cells, dt,
                        s->buf<double>(B_SWITCH_TIME), s->buf<int32_t>(B_FACE_PTR),
                        s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0), s->buf<uint8_t>(s->cur_go ? B_GO0 : B_GO1),
-                       s->buf<double>(s->cur_t ? B_T1 : B_T0), s->buf<double>(s->cur_t ? B_T0 : B_T1), stream);
+                       s->buf<double>(s->cur_t ? B_T1 : B_T0), s->buf<double>(s->cur_t ? B_T0 : B_T1),
+                       s->buf<int2>(B_LIGHT_CELLINFO), s->buf<CellDynT>(B_CELL_DYN), s->cur_go ^ 1, stream);
     s->cur_go ^= 1; s->cur_t ^= 1; s->launches++;
+}
+
+// the caller replaced the face states (Cars.update with a foreign lights DataFrame): refresh the per-bin go words
+void sync_go_words(tb2_sim* s, cudaStream_t stream) {
+    if (!s->go_dirty) return;
+    const tb2_config& c = s->cfg;
+    launch_rebuild_go_words(c.n_replicas * c.n_lights, c.n_lights > 0 ? c.n_lights : 1, c.n_faces, s->n_cells,
+                            s->buf<int32_t>(B_FACE_PTR), s->buf<uint8_t>(s->cur_go ? B_GO1 : B_GO0),
+                            s->buf<int2>(B_LIGHT_CELLINFO), s->buf<CellDynT>(B_CELL_DYN), s->cur_go, stream);
+    s->go_dirty = false;
+    s->launches++;
 }
 
 template <typename R>
 void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
-    const size_t C2 = (size_t)2 * s->n_cells * s->cfg.n_replicas;
     StepArgsT<R> a{};
     fill_args<R>(s, &a);
     a.dt = (R)dt;
     a.dt64 = dt;
     a.tick = tick;
     a.write_aux = aux;
-    int32_t* tab = s->buf<int32_t>(B_TAB);
-    a.tab_cur = reinterpret_cast<const int2*>(tab + C2 * s->cur_tab);
-    a.tab_next = tab + C2 * ((s->cur_tab + 1) % 3);
-    a.tab_clear = tab + C2 * ((s->cur_tab + 2) % 3);
     a.skip_insert = s->cfg.neighbor_mode == TB2_NEIGHBOR_SORT;
     launch_step(a, stream);
     if (a.skip_insert)   // north_star's pipeline: radix sort by bin + segment heads -> the same table
         s->launches += neighbor_sort_build(a.n_cars, a.cars_per_replica, s->n_cells, key_bits_of(s->cfg), a.cell,
                                            s->buf<int32_t>(B_SORT_KEYS_IN), s->buf<int32_t>(B_SORT_VALS_IN),
                                            s->buf<int32_t>(B_SORT_KEYS_OUT), s->buf<int32_t>(B_SORT_VALS_OUT),
-                                           s->buf<char>(B_SORT_TEMP), s->lay.bytes[B_SORT_TEMP], a.tab_next, stream);
+                                           s->buf<char>(B_SORT_TEMP), s->lay.bytes[B_SORT_TEMP], a.cell_dyn, a.tab_next_k, stream);
 }
 
 // All n_steps of a batch in one launch of the persistent cluster kernel (small worlds only).
 template <typename R>
 cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cudaStream_t stream) {
     using R2 = typename real2<R>::type;
-    const size_t C2 = (size_t)2 * s->n_cells * s->cfg.n_replicas;
     StepArgsT<R> a{};
     fill_args<R>(s, &a);
     a.dt = (R)dt;
@@ -282,7 +295,6 @@ cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cud
     a.skip_insert = 0;
     PersistArgsT<R> pa{};
     pa.pos[0] = s->buf<R2>(B_POS0); pa.pos[1] = s->buf<R2>(B_POS1);
-    for (int k = 0; k < 3; ++k) pa.tab[k] = s->buf<int32_t>(B_TAB) + C2 * k;
     pa.go[0] = s->buf<uint8_t>(B_GO0); pa.go[1] = s->buf<uint8_t>(B_GO1);
     pa.t[0] = s->buf<double>(B_T0); pa.t[1] = s->buf<double>(B_T1);
     pa.cur_pos = s->cur_pos; pa.cur_tab = s->cur_tab; pa.cur_go = s->cur_go; pa.cur_t = s->cur_t;
@@ -293,6 +305,7 @@ cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cud
 // Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
 // aux: also write the columns nobody can observe between steps (velocity, distances, leader, start-of-step bin).
 void step_cars(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) {
+    sync_go_words(s, stream);
     if (s->cfg.precision == TB2_F64) step_cars_t<double>(s, dt, tick, aux, stream);
     else step_cars_t<float>(s, dt, tick, aux, stream);
     s->launches++;
@@ -388,6 +401,7 @@ int tb2_upload(tb2_sim* s, int field, const void* src, size_t bytes, void* strea
         field == TB2_PATH_EFF_END || field == TB2_DEST_XY ||
         field == TB2_FACE_VEC || field == TB2_LIGHT_XY || field == TB2_FACE_PTR || field == TB2_CELL_LIGHT_PTR ||
         field == TB2_CELL_LIGHT_IDX) s->prepared = false;
+    if (field == TB2_FACE_GO) s->go_dirty = true;
     return TB2_OK;
 }
 
@@ -415,16 +429,15 @@ int tb2_prepare(tb2_sim* s, void* stream_) {
     if (s->cfg.precision == TB2_F64) {
         StepArgs64 a{};
         fill_args<double>(s, &a);
-        launch_prepare(a, s->buf<double2>(B_PT_CURV), s->buf<double2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
-                       s->cur_tab, stream);
+        launch_prepare(a, s->buf<double2>(B_PT_CURV), s->buf<double2>(B_FACE_UNIT), s->cfg.n_faces, stream);
     } else {
         StepArgs32 a{};
         fill_args<float>(s, &a);
-        launch_prepare(a, s->buf<float2>(B_PT_CURV), s->buf<float2>(B_FACE_UNIT), s->cfg.n_faces, s->buf<int32_t>(B_TAB),
-                       s->cur_tab, stream);
+        launch_prepare(a, s->buf<float2>(B_PT_CURV), s->buf<float2>(B_FACE_UNIT), s->cfg.n_faces, stream);
     }
-    s->launches += 2 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0);
+    s->launches += 2 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0) + (s->cfg.n_lights > 0 ? 2 : 0);
     CU(cudaGetLastError());
+    s->go_dirty = false;
     s->prepared = true;
     return TB2_OK;
 }
@@ -453,6 +466,7 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
     if (s->allow_persistent && n_steps >= 2 && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC &&
         (int64_t)s->cfg.n_cars * s->cfg.n_replicas <= persistent_max_cars(s->cfg.precision == TB2_F32)) {
         // small world: the whole batch is one launch of the persistent cluster kernel
+        sync_go_words(s, stream);
         const cudaError_t pe = s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, n_steps, order, stream)
                                                            : step_persistent_t<float>(s, dt, n_steps, order, stream);
         if (pe == cudaErrorCooperativeLaunchTooLarge) {   // the device is shared: fall back to one launch per step for good

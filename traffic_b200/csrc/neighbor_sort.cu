@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(int n_cars, int cars_per
 
 // one thread per sorted slot; the left neighbour's key comes from a warp shuffle (lane 0 reads it from memory)
 __global__ void __launch_bounds__(256) segment_heads_kernel(int n_cars, const int32_t* __restrict__ keys,
-                                                            const int32_t* __restrict__ vals, int32_t* __restrict__ tab) {
+                                                            const int32_t* __restrict__ vals, CellDynT* __restrict__ dyn,
+                                                            int table_k) {
     const int p = (int)blockIdx.x * 256 + (int)threadIdx.x;
     const bool in = p < n_cars;
     const int key = in ? keys[p] : -1;
@@ -35,8 +36,8 @@ __global__ void __launch_bounds__(256) segment_heads_kernel(int n_cars, const in
         right_val = (p + 1 < n_cars) ? vals[p + 1] : TB2_EMPTY;
     }
     if (in && key != left) {   // head of a segment: first car of the bin, and the next slot if it is the same bin
-        tab[2 * key] = vals[p];
-        tab[2 * key + 1] = (right_key == key) ? right_val : TB2_EMPTY;
+        dyn[key].w[2 * table_k] = vals[p];
+        dyn[key].w[2 * table_k + 1] = (right_key == key) ? right_val : TB2_EMPTY;
     }
 }
 
@@ -49,14 +50,14 @@ size_t neighbor_sort_temp_bytes(int n_cars, int key_bits) {
     return bytes;
 }
 
-// tab must already be cleared (all TB2_EMPTY).  Returns the number of kernel launches issued (CUB's included, estimated).
+// table_k of cell_dyn must already be cleared (all TB2_EMPTY).  Returns the number of kernel launches issued (CUB's included, estimated).
 int neighbor_sort_build(int n_cars, int cars_per_replica, int n_cells, int key_bits, const int32_t* cell,
                         int32_t* keys_in, int32_t* vals_in, int32_t* keys_out, int32_t* vals_out, void* temp,
-                        size_t temp_bytes, int32_t* tab, cudaStream_t stream) {
+                        size_t temp_bytes, CellDynT* cell_dyn, int table_k, cudaStream_t stream) {
     if (n_cars <= 0) return 0;
     const int blocks = (n_cars + 255) / 256;
     sort_keys_kernel<<<blocks, 256, 0, stream>>>(n_cars, cars_per_replica, n_cells, cell, keys_in, vals_in);
     cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n_cars, 0, key_bits, stream);
-    segment_heads_kernel<<<blocks, 256, 0, stream>>>(n_cars, keys_out, vals_out, tab);
+    segment_heads_kernel<<<blocks, 256, 0, stream>>>(n_cars, keys_out, vals_out, cell_dyn, table_k);
     return 2 + 3;
 }

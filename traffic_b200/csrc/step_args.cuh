@@ -21,15 +21,33 @@ struct GridArgsT {
     R inv_exd, inv_eyd;              // 1/ed, only used for the index estimate
 };
 
-// Per-cell light record, fetched in the same dependent-load wave as the cell's car-table entry: the CSR range of the
-// cell's lights plus the first light inline (position, id, face range), so the common "0 or 1 light in my bin" case
-// needs no further pointer chasing before the linspace test.  Built once by the prepare kernel.
-template <typename R>
-struct alignas(32) CellLightsT {   // exactly one 32-byte sector
-    int32_t lb;          // first entry of the cell in cell_light_idx
-    int32_t counts;      // (number of lights in the cell) | (number of faces of the first light) << 16
-    int32_t fb0, pad;    // first light: its first face
-    typename real2<R>::type xy0;   // first light: position
+// Per-cell records.  Everything a car needs from its 200 m bin is addressable from the bin id alone and arrives in ONE
+// dependent-load wave (two 32-byte sectors):
+//
+//  CellDynT  (per replica x cell, rewritten every step): the three rotating (smallest, second smallest) car-index tables
+//            - read / being filled for the next step / being cleared - side by side, plus the double-buffered "go word"
+//            of the cell's first light, so the table entry, the prefetched next-table entry (table_insert's skip test)
+//            and the light-face states share a sector.
+//  CellStatT (per cell, static, shared by replicas): position of the cell's first light and the unit vectors of its
+//            first four faces quantised to snorm16 - enough for the filtered anti-parallel test (the exact fp64 test
+//            runs only inside the filter's band and fetches face_unit[] then).
+//
+// go word: bits 0-7 = go state of faces 0..7 of the cell's first light, bits 8-15 = its face count (clipped to 255),
+//          bits 16-31 = number of lights in the cell (clipped to 65535).  Written by the lights tick / rebuild kernel.
+struct alignas(32) CellDynT {
+    int32_t w[8];   // [2k], [2k+1]: table k (min, second-min);  [6], [7]: go word of face-state buffer 0 / 1
+};
+#define TB2_DYN_GO 6
+
+template <typename R> struct CellStatT;
+template <> struct alignas(32) CellStatT<double> {
+    double2 xy0;       // first light of the cell: position
+    int16_t fu[8];     // its first four faces: round(unit_vector * 32767)  (x0, y0, x1, y1, ...)
+};
+template <> struct alignas(32) CellStatT<float> {
+    float2 xy0;
+    int16_t fu[8];
+    int32_t pad[2];
 };
 
 template <typename R>
@@ -64,10 +82,11 @@ struct StepArgsT {
     int32_t* cell;         // bin of the current position; updated in place by the owning thread
     int32_t* cell_prev;    // aux: bin of the start-of-step position (the reference's xbin/ybin columns)
     int32_t* leader;       // aux
-    // cell -> (smallest, second smallest) car index; three rotating tables
-    const int2* tab_cur;
-    int32_t* tab_next;
-    int32_t* tab_clear;
+    // per replica x cell dynamic record (see CellDynT): which of the three tables is read / filled / cleared this step,
+    // and which go-word slot belongs to go_cur / go_next
+    CellDynT* cell_dyn;
+    int32_t tab_cur_k, tab_next_k, tab_clear_k;
+    int32_t go_k_cur;
     // lights
     const R2* light_xy;
     const int32_t* face_ptr;
@@ -76,7 +95,8 @@ struct StepArgsT {
     const uint8_t* go_cur;
     const int32_t* cell_light_ptr;
     const int32_t* cell_light_idx;
-    CellLightsT<R>* cell_lights;   // [n_cells] derived from the CSR + light arrays at prepare time
+    CellStatT<R>* cell_stat;       // [n_cells] derived from the CSR + light arrays at prepare time
+    int2* light_cellinfo;          // [L] (cell id if the light is the first of its cell else -1, static bits of the go word)
     // fused TrafficLights.update (cars.py:123-133), runs in the trailing blocks when tick != 0
     int32_t tick, pad;
     const double* switch_time;
@@ -93,7 +113,6 @@ struct StepArgsT {
 template <typename R>
 struct PersistArgsT {
     typename real2<R>::type* pos[2];
-    int32_t* tab[3];
     uint8_t* go[2];
     double* t[2];
     int32_t cur_pos, cur_tab, cur_go, cur_t;
@@ -112,17 +131,20 @@ cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& p
 cudaError_t launch_persistent(const StepArgs32& a, const PersistArgsT<float>& pa, cudaStream_t stream);
 // (re)derive everything the step kernel keeps cached from the uploaded state: per-point curvature constants, per-car
 // head point + constants, unit face vectors, bins, and the cell table `cur_table` of the three in tab3 (all reset).
-void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3, int cur_table,
-                    cudaStream_t stream);
-void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, int32_t* tab3, int cur_table,
-                    cudaStream_t stream);
-static_assert(sizeof(CellLightsT<double>) == 32 && sizeof(CellLightsT<float>) == 32, "CellLightsT layout");
+void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, cudaStream_t stream);
+void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, cudaStream_t stream);
+// re-derive the go words of the CURRENT face-state buffer (after tb2_upload(TB2_FACE_GO) / prepare)
+void launch_rebuild_go_words(int n_lights_total, int lights_per_replica, int faces_per_replica, int n_cells,
+                             const int32_t* face_ptr, const uint8_t* go_cur, const int2* light_cellinfo, CellDynT* cell_dyn,
+                             int go_k, cudaStream_t stream);
+static_assert(sizeof(CellStatT<double>) == 32 && sizeof(CellStatT<float>) == 32 && sizeof(CellDynT) == 32, "cell record layout");
 // sort-based neighbour source (neighbor_sort.cu)
 size_t neighbor_sort_temp_bytes(int n_cars, int key_bits);
 int neighbor_sort_build(int n_cars, int cars_per_replica, int n_cells, int key_bits, const int32_t* cell, int32_t* keys_in,
                         int32_t* vals_in, int32_t* keys_out, int32_t* vals_out, void* temp, size_t temp_bytes,
-                        int32_t* tab, cudaStream_t stream);
+                        CellDynT* cell_dyn, int table_k, cudaStream_t stream);
 // TrafficLights.update alone (fp64 regardless of the car arithmetic)
-void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_per_replica, double dt,
+void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_per_replica, int n_cells, double dt,
                         const double* switch_time, const int32_t* face_ptr, const uint8_t* go_cur, uint8_t* go_next,
-                        const double* t_cur, double* t_next, cudaStream_t stream);
+                        const double* t_cur, double* t_next, const int2* light_cellinfo, CellDynT* cell_dyn, int go_k_next,
+                        cudaStream_t stream);

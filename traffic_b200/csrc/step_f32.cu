@@ -10,7 +10,6 @@ cudaError_t launch_persistent(const StepArgs32& a, const PersistArgsT<float>& pa
     return tb2k::launch_persistent_t<float>(a, pa, stream);
 }
 
-void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, int32_t* tab3, int cur_table,
-                    cudaStream_t stream) {
-    tb2k::launch_prepare_t<float>(a, pt_curv, face_unit, n_faces, tab3, cur_table, stream);
+void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, cudaStream_t stream) {
+    tb2k::launch_prepare_t<float>(a, pt_curv, face_unit, n_faces, stream);
 }

@@ -4,12 +4,13 @@
 
 namespace {
 __global__ void __launch_bounds__(256) lights_tick_kernel(int n_lights, int lights_per_replica, int faces_per_replica,
-                                                          double dt, const double* switch_time, const int32_t* face_ptr,
-                                                          const uint8_t* go_cur, uint8_t* go_next, const double* t_cur,
-                                                          double* t_next) {
+                                                          int n_cells, double dt, const double* switch_time,
+                                                          const int32_t* face_ptr, const uint8_t* go_cur, uint8_t* go_next,
+                                                          const double* t_cur, double* t_next, const int2* light_cellinfo,
+                                                          CellDynT* cell_dyn, int go_k_next) {
     const int l = (int)blockIdx.x * 256 + (int)threadIdx.x;
-    tb2k::lights_tick_body(l, n_lights, lights_per_replica, faces_per_replica, dt, switch_time, face_ptr, go_cur, go_next,
-                           t_cur, t_next);
+    tb2k::lights_tick_body(l, n_lights, lights_per_replica, faces_per_replica, n_cells, dt, switch_time, face_ptr, go_cur,
+                           go_next, t_cur, t_next, light_cellinfo, cell_dyn, go_k_next);
 }
 }  // namespace
 
@@ -28,15 +29,24 @@ cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& p
     return tb2k::launch_persistent_t<double>(a, pa, stream);
 }
 
-void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, int32_t* tab3, int cur_table,
-                    cudaStream_t stream) {
-    tb2k::launch_prepare_t<double>(a, pt_curv, face_unit, n_faces, tab3, cur_table, stream);
+void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, cudaStream_t stream) {
+    tb2k::launch_prepare_t<double>(a, pt_curv, face_unit, n_faces, stream);
 }
 
-void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_per_replica, double dt,
+void launch_rebuild_go_words(int n_lights_total, int lights_per_replica, int faces_per_replica, int n_cells,
+                             const int32_t* face_ptr, const uint8_t* go_cur, const int2* light_cellinfo, CellDynT* cell_dyn,
+                             int go_k, cudaStream_t stream) {
+    if (n_lights_total <= 0) return;
+    tb2k::rebuild_go_words_kernel<<<(n_lights_total + 255) / 256, 256, 0, stream>>>(
+        n_lights_total, lights_per_replica, faces_per_replica, n_cells, face_ptr, go_cur, light_cellinfo, cell_dyn, go_k);
+}
+
+void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_per_replica, int n_cells, double dt,
                         const double* switch_time, const int32_t* face_ptr, const uint8_t* go_cur, uint8_t* go_next,
-                        const double* t_cur, double* t_next, cudaStream_t stream) {
+                        const double* t_cur, double* t_next, const int2* light_cellinfo, CellDynT* cell_dyn, int go_k_next,
+                        cudaStream_t stream) {
     const int blocks = (n_lights_total + 255) / 256 > 0 ? (n_lights_total + 255) / 256 : 1;
-    lights_tick_kernel<<<blocks, 256, 0, stream>>>(n_lights_total, lights_per_replica, faces_per_replica, dt, switch_time,
-                                                   face_ptr, go_cur, go_next, t_cur, t_next);
+    lights_tick_kernel<<<blocks, 256, 0, stream>>>(n_lights_total, lights_per_replica, faces_per_replica, n_cells, dt,
+                                                   switch_time, face_ptr, go_cur, go_next, t_cur, t_next, light_cellinfo,
+                                                   cell_dyn, go_k_next);
 }

@@ -235,18 +235,24 @@ __device__ __forceinline__ typename real2<R>::type curv_constants(const typename
     return mk2(s, log_(free_d / s));
 }
 
-// models.determine_anti_parallel_vectors over the red faces of light l  (navigation.py:481-489, models.py:90-97).
+// models.determine_anti_parallel_vectors  (navigation.py:481-489, models.py:90-97).
 // face_unit holds unit_vector(face) = face / norm(face), computed once by the prepare kernel with the reference's
 // expression.  np.isclose(pi, angle, atol=0.1) is true iff angle >= T = (pi - 0.1) / (1 + 1e-5); acos is monotone, so
-// the cosine decides: an fp32 cosine when it is further than 1e-4 from cos(T), the reference's fp64 expression
-// otherwise, and acos itself only inside a +-1e-6 band.  Float mode: the fp32 cosine decides.
-static __device__ __noinline__ bool antiparallel_exact(double cvx, double cvy, double2 fu) {
-    const double ncv = norm2<double>(cvx, cvy);
-    const double c = clip1<double>(dot2<double>(cvx / ncv, cvy / ncv, fu.x, fu.y));
-    if (c < K<double>::cosT - 1.0e-6) return true;
-    if (c > K<double>::cosT + 1.0e-6) return false;
-    return isclose_<double>(K<double>::pi, acos(c), 1.0e-5, 0.1);
+// the cosine decides: an fp32 cosine when it is further than the filter band from cos(T), the reference's expression
+// otherwise, and acos itself only inside a +-1e-6 band.
+template <typename R>
+static __device__ __noinline__ bool antiparallel_exact(R cvx, R cvy, typename real2<R>::type fu) {
+    const R ncv = norm2<R>(cvx, cvy);
+    const R c = clip1<R>(dot2<R>(cvx / ncv, cvy / ncv, fu.x, fu.y));
+    if (c < K<R>::cosT - R(1.0e-6)) return true;
+    if (c > K<R>::cosT + R(1.0e-6)) return false;
+    return isclose_<R>(K<R>::pi, acos_(c), R(1.0e-5), R(0.1));
 }
+// Band of the fp32 cosine filter.  Error budget: snorm16 face units (<= 2.2e-5), fp32 rounding of the light-car vector
+// at UTM-scale differences, rsqrtf and the dot product (< 1e-5 together).
+#define TB2_COS_BAND 1.5e-4f
+
+// Red faces of light l (general path: per-face bytes + fp64/fp32 unit vectors from memory)
 template <typename R>
 __device__ __forceinline__ bool red_face_ahead(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fb, int fe,
                                                int fbase, R cvx, R cvy) {
@@ -257,21 +263,55 @@ __device__ __forceinline__ bool red_face_ahead(const StepArgsT<R>& a, const uint
         if (go_cur[fbase + f]) continue;
         const typename real2<R>::type fu = a.face_unit[f];
         const float c = (fx * (float)fu.x + fy * (float)fu.y) * inv;
-        if constexpr (is_f64<R>) {
-            if (c < (float)K<double>::cosT - 1.0e-4f) found = true;
-            else if (!(c > (float)K<double>::cosT + 1.0e-4f)) found = antiparallel_exact(cvx, cvy, fu);
-        } else {
-            found = c <= K<float>::cosT;
-        }
+        if (c < (float)K<double>::cosT - TB2_COS_BAND) found = true;
+        else if (!(c > (float)K<double>::cosT + TB2_COS_BAND)) found = antiparallel_exact<R>(cvx, cvy, fu);
     }
     return found;
 }
 
+// navigation.light_obstacles (navigation.py:459-498) over the lights first, first+1, ... of bin c through the static
+// cell -> lights CSR: the rare general path (a second light in the bin, or a first light with more than four faces).
+// Returns the distance to the first red anti-parallel face's light, +0 for False (a light off the linspace), -0 for
+// None (lights exhausted).
+template <typename R>
+static __device__ __noinline__ R light_scan_general(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fbase,
+                                                    int c, int first, R x, R tx, R y, R ty) {
+    const Axis<R> ax = make_axis<R>(x, tx), ay = make_axis<R>(y, ty);
+    const int lb = a.cell_light_ptr[c], le = a.cell_light_ptr[c + 1];
+    for (int q = lb + first; q < le; ++q) {
+        const int l = a.cell_light_idx[q];
+        const typename real2<R>::type lp = a.light_xy[l];
+        if (!(on_axis(ax, 1, lp.x, a.origin_x) && on_axis(ay, 1, lp.y, a.origin_y))) return R(0);
+        const R cvx = lp.x - x, cvy = lp.y - y;
+        if (red_face_ahead<R>(a, go_cur, a.face_ptr[l], a.face_ptr[l + 1], fbase, cvx, cvy)) return norm2<R>(cvx, cvy);
+    }
+    return -R(0);
+}
+
+// exact re-evaluation of the first light's faces that fell into the filter band (bit k of `band` = face k)
+template <typename R>
+static __device__ __noinline__ bool first_light_band_exact(const StepArgsT<R>& a, int c, uint32_t band, R cvx, R cvy) {
+    const int fb0 = a.face_ptr[a.cell_light_idx[a.cell_light_ptr[c]]];
+    bool found = false;
+    for (int k = 0; k < 4; ++k)
+        if ((band >> k) & 1u) found = found || antiparallel_exact<R>(cvx, cvy, a.face_unit[fb0 + k]);
+    return found;
+}
+
+// go word of a light's faces (see step_args.cuh): bit k = go state of face k, k < 8
+__device__ __forceinline__ uint32_t go_mask_of(const uint8_t* __restrict__ go, int fb, int fe) {
+    uint32_t m = 0;
+    for (int f = fb, k = 0; f < fe && k < 8; ++f, ++k) m |= (go[f] ? 1u : 0u) << k;
+    return m;
+}
+
 // TrafficLights.update  (cars.py:130-133); lg runs over replicas x lights, geometry (face_ptr) is shared.  Always fp64.
+// Also refreshes the go word of the bin whose first light this is (next face-state buffer).
 __device__ __forceinline__ void lights_tick_body(int lg, int n_lights_total, int lights_per_replica, int faces_per_replica,
-                                                 double dt, const double* __restrict__ switch_time,
+                                                 int n_cells, double dt, const double* __restrict__ switch_time,
                                                  const int32_t* __restrict__ face_ptr, const uint8_t* __restrict__ go_cur,
-                                                 uint8_t* __restrict__ go_next, const double* t_cur, double* t_next) {
+                                                 uint8_t* __restrict__ go_next, const double* t_cur, double* t_next,
+                                                 const int2* __restrict__ light_cellinfo, CellDynT* cell_dyn, int go_k_next) {
     const double t = __dadd_rn(*t_cur, dt);
     if (lg == 0) *t_next = t;
     if (lg >= n_lights_total) return;
@@ -282,102 +322,149 @@ __device__ __forceinline__ void lights_tick_body(int lg, int n_lights_total, int
     if (r != 0.0 && ((sw < 0.0) != (r < 0.0))) r = __dadd_rn(r, sw);
     // isclose(0, r, rtol=1e-4): |0 - r| <= 1e-8 + 1e-4*|r|
     const bool s = ((fabs(r) <= __dadd_rn(1.0e-8, __dmul_rn(1.0e-4, fabs(r)))) && isfinite(r)) || (r == 0.0);
-    for (int f = face_ptr[l]; f < face_ptr[l + 1]; ++f) go_next[fbase + f] = s ? (uint8_t)!go_cur[fbase + f] : go_cur[fbase + f];
+    uint32_t mask = 0;
+    const int fb = face_ptr[l], fe = face_ptr[l + 1];
+    for (int f = fb; f < fe; ++f) {
+        const uint8_t g = s ? (uint8_t)!go_cur[fbase + f] : go_cur[fbase + f];
+        go_next[fbase + f] = g;
+        if (f - fb < 8) mask |= (g ? 1u : 0u) << (f - fb);
+    }
+    const int2 info = light_cellinfo[l];
+    if (info.x >= 0) cell_dyn[(size_t)rep * n_cells + info.x].w[TB2_DYN_GO + go_k_next] = (int32_t)((uint32_t)info.y | mask);
 }
 
-__device__ __forceinline__ void table_insert(int32_t* tab, int cell, int i) {
-    // Entries only ever decrease while a table is being filled, so a car whose index already exceeds the bin's current
-    // second-smallest entry can never end up among the first two: it skips both atomics.  CTAs run roughly in index
-    // order, so after the first couple of cars of a bin almost everybody skips - no same-address serialisation in L2 and
-    // no wait for the atomic's return value.  (The read bypasses L1; a stale value is only larger, i.e. conservative.)
-    if (i > __ldcg(&tab[2 * cell + 1])) return;
-    const int old = atomicMin(&tab[2 * cell], i);
+// Insert car i into table slot `t` (= &cell_dyn[bin].w[2k]) of the step being prepared.
+// Entries only ever decrease while a table is being filled, so a car whose index already exceeds the bin's current
+// second-smallest entry can never end up among the first two: it skips both atomics.  CTAs run roughly in index order,
+// so after the first couple of cars of a bin almost everybody skips - no same-address serialisation in L2 and no wait
+// for the atomic's return value.  `sec` is a (possibly stale, hence only larger = conservative) copy of t[1]; the step
+// kernel prefetches it together with the bin's current-table entry, long before the new bin is known (a car stays in
+// its bin in ~99 % of the steps).
+__device__ __forceinline__ void table_insert(int32_t* t, int i, int sec) {
+    if (i > sec) return;
+    const int old = atomicMin(t, i);
     const int loser = old > i ? old : i;   // whoever is not the cell minimum competes for second place
-    if (loser != TB2_EMPTY) atomicMin(&tab[2 * cell + 1], loser);
+    if (loser != TB2_EMPTY) atomicMin(t + 1, loser);
 }
 
-// The buffers that rotate from step to step (ping-pong positions, the three cell tables, double-buffered faces).
+// What rotates from step to step: ping-pong positions, which of the three tables is read / filled, face-state buffer.
 template <typename R>
 struct Rot {
     const typename real2<R>::type* pos_in;
     typename real2<R>::type* pos_out;
-    const int2* tab_cur;
-    int32_t* tab_next;
     const uint8_t* go_cur;
+    int32_t tab_cur_k, tab_next_k, go_k_cur;
     int32_t step_index;
 };
 
-// One car, one step.  AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell tables /
-// face states, agent arrival bookkeeping); a single simulation compiles these out.
-template <typename R, bool AUX, bool ENS>
-__device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& rot, const int i) {
+// ---------------------------------------------------------------------------------------------------------------
+// One car, one step, in three segments so that the same arithmetic serves the one-launch-per-step kernel, the
+// persistent small-world kernels (registers filled by plain loads) and the software-pipelined big-world kernel
+// (operands staged in shared memory by cp.async, see pipe_kernel):
+//   seg_view   : FrontView - crossed-node test, target, distance-to-node, the two linspace axes
+//   seg_detect : leader lookup + red-light scan
+//   seg_move   : speed factor, velocity law, stall push, route advance, Euler step, bin + table insertion, bookkeeping
+// AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell records / face states, agent
+// arrival bookkeeping); a single simulation compiles these out.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+struct View {
+    R x, y, tx, ty, dx, dy, d_node;
+    int nx, ny;          // int(|dx|), int(|dy|): lengths of the two linspaces
+    bool has_path, crossed, spaces;
+    int path_len;
+};
+
+template <typename R>
+__device__ __forceinline__ View<R> seg_view(const StepArgsT<R>& a, int i, typename real2<R>::type p,
+                                            typename real2<R>::type head, int cur, int end, int eff) {
     using R2 = typename real2<R>::type;
-    // replica of this car (1 for a single simulation): offsets into the per-replica cell tables and face states
-    const int rep = ENS ? i / a.cars_per_replica : 0;
-    const int cbase = rep * a.g.n_cells, fbase = rep * a.faces_per_replica, ibase = rep * a.cars_per_replica;
-
-    // ---- independent loads first ----
-    const R2 p = rot.pos_in[i];
-    const int cur = a.cursor[i];
-    const int end = a.path_end[i];
-    const int eff = a.path_eff_end[i];
-    const int c = a.cell[i];
-    const R2 head = a.head_xy[i];
-    const R2 hc = a.head_curv[i];
-    const R rt = a.route_time[i];
-    // ---- dependent on the bin ----
-    const int2 m = rot.tab_cur[cbase + c];
-    const CellLightsT<R> cl = a.cell_lights[c];
-    const int lb = cl.lb, le = cl.lb + (cl.counts & 0xffff);
-
-    const R x = p.x, y = p.y;
-    const bool has_path = cur < eff;
-    const int path_len = has_path ? end - cur : 0;
+    View<R> v;
+    v.x = p.x; v.y = p.y;
+    v.has_path = cur < eff;
+    v.path_len = v.has_path ? end - cur : 0;
     // FrontView.crossed_node_event (navigation.py:91-111): tolerance relative to the car's ABSOLUTE coordinate
-    const bool crossed = has_path & isclose_abs<R>(head.x, x, x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
-                         isclose_abs<R>(head.y, y, y + a.origin_y, R(1.0e-5), R(1.0e-8));
+    v.crossed = v.has_path & isclose_abs<R>(head.x, v.x, v.x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
+                isclose_abs<R>(head.y, v.y, v.y + a.origin_y, R(1.0e-5), R(1.0e-8));
     // target (FrontView.upcoming_node_position, navigation.py:73-89).  head_xy holds the destination once the route is
-    // exhausted (written below / by prepare), so a parked car needs no extra load; only the step that crosses the last
-    // route point fetches dest_xy, and a crossing step fetches the next route point.
+    // exhausted (written by seg_move / prepare), so a parked car needs no extra load; only the step that crosses the
+    // last route point fetches dest_xy, and a crossing step fetches the next route point.
     R2 t = head;
-    if (crossed) t = (path_len < 2) ? a.dest_xy[i] : a.path_xy[cur + 1];
+    if (v.crossed) t = (v.path_len < 2) ? a.dest_xy[i] : a.path_xy[cur + 1];
+    v.tx = t.x; v.ty = t.y;
+    v.dx = t.x - v.x; v.dy = t.y - v.y;
+    v.d_node = norm2<R>(v.dx, v.dy);
+    const Axis<R> ax = make_axis<R>(v.x, v.tx), ay = make_axis<R>(v.y, v.ty);
+    v.nx = ax.n; v.ny = ay.n;
+    v.spaces = axis_any<R>(ax, a.origin_x) && axis_any<R>(ay, a.origin_y);
+    return v;
+}
 
-    const R dx = t.x - x, dy = t.y - y;
-    const R d_node = norm2<R>(dx, dy);
-    const Axis<R> ax = make_axis<R>(x, t.x), ay = make_axis<R>(y, t.y);
-    const bool spaces = axis_any<R>(ax, a.origin_x) && axis_any<R>(ay, a.origin_y);
+template <typename R>
+__device__ __forceinline__ Axis<R> axis_of(R start, R stop, R delta, int n) {
+    Axis<R> ax;
+    ax.start = start; ax.stop = stop; ax.delta = delta; ax.n = n;
+    return ax;
+}
 
-    // ---- leader lookup (navigation.car_obstacles) ----
-    R d_car = R(0);
-    int lead = -1;
-    const int j = (m.x != i) ? m.x : m.y;
-    if (spaces && j != TB2_EMPTY) {
-        const R2 o = rot.pos_in[j];
+// navigation.car_obstacles (navigation.py:422-456) against candidate j at position o, then navigation.light_obstacles
+// (navigation.py:459-498) for a bin whose go word is gw; load_stat() yields the bin's static light record.
+template <typename R, typename LoadStat>
+__device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fbase, int c,
+                                           const View<R>& v, int j, typename real2<R>::type o, uint32_t gw,
+                                           LoadStat load_stat, R& d_car, int& lead, R& d_light) {
+    const Axis<R> ax = axis_of<R>(v.x, v.tx, v.dx, v.nx), ay = axis_of<R>(v.y, v.ty, v.dy, v.ny);
+    d_car = R(0);
+    lead = -1;
+    if (v.spaces && j != TB2_EMPTY) {
         if (on_axis(ax, 0, o.x, a.origin_x) && on_axis(ay, 0, o.y, a.origin_y)) {
-            d_car = norm2<R>(o.x - x, o.y - y);
+            d_car = norm2<R>(o.x - v.x, o.y - v.y);
             if (d_car != R(0)) lead = j;
         }
     }
-    // ---- red-light scan (navigation.light_obstacles) ----
-    R d_light = R(0);
-    if (spaces && lb < le) {
-        d_light = -R(0);  // loop exhausted -> None
-        for (int q = lb; q < le; ++q) {
-            // the first light of the bin came with the cell record; further ones (rare) go through the CSR
-            const int l = (q == lb) ? -1 : a.cell_light_idx[q];
-            const R2 lp = (q == lb) ? cl.xy0 : a.light_xy[l];
-            if (on_axis(ax, 1, lp.x, a.origin_x) && on_axis(ay, 1, lp.y, a.origin_y)) {
-                const R cvx = lp.x - x, cvy = lp.y - y;
-                const int fb = (q == lb) ? cl.fb0 : a.face_ptr[l];
-                const int fe = (q == lb) ? cl.fb0 + (cl.counts >> 16) : a.face_ptr[l + 1];
-                if (red_face_ahead<R>(a, rot.go_cur, fb, fe, fbase, cvx, cvy)) { d_light = norm2<R>(cvx, cvy); break; }
-            } else { d_light = R(0); break; }
+    d_light = R(0);
+    const int nl = (int)(gw >> 16), nf0 = (int)((gw >> 8) & 0xffu);
+    if (v.spaces && nl) {
+        if (nf0 > 4) {
+            d_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, v.tx, v.y, v.ty);
+        } else {
+            const CellStatT<R> st = load_stat();
+            if (on_axis(ax, 1, st.xy0.x, a.origin_x) && on_axis(ay, 1, st.xy0.y, a.origin_y)) {
+                // first light of the bin: faces from the static record (snorm16 units), go bits from the go word
+                const R cvx = st.xy0.x - v.x, cvy = st.xy0.y - v.y;
+                const float fx = (float)cvx, fy = (float)cvy;
+                const float inv = rsqrtf(fx * fx + fy * fy) * (1.0f / 32767.0f);
+                const uint32_t red = ~gw & ((1u << nf0) - 1u);
+                bool found = false;
+                uint32_t band = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float cs = (fx * (float)st.fu[2 * k] + fy * (float)st.fu[2 * k + 1]) * inv;
+                    const bool is_red = (red >> k) & 1u;
+                    const bool yes = cs < (float)K<double>::cosT - TB2_COS_BAND;
+                    const bool no = cs > (float)K<double>::cosT + TB2_COS_BAND;
+                    found = found || (is_red && yes);
+                    if (is_red && !yes && !no) band |= 1u << k;
+                }
+                if (!found && band) found = first_light_band_exact<R>(a, c, band, cvx, cvy);
+                if (found) d_light = norm2<R>(cvx, cvy);
+                else if (nl > 1) d_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, v.tx, v.y, v.ty);
+                else d_light = -R(0);   // lights exhausted -> None
+            }
         }
     }
+}
 
+template <typename R, bool AUX, bool ENS>
+__device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& rot, int i, int rep, const View<R>& v,
+                                         R d_car, int lead, R d_light, typename real2<R>::type hc, R rt, int cur, int end,
+                                         int eff, int c, int sec_next) {
+    using R2 = typename real2<R>::type;
+    const int cbase = rep * a.g.n_cells, ibase = rep * a.cars_per_replica;
+    const R x = v.x, y = v.y, d_node = v.d_node;
     // ---- velocity law + route advance (simulation.update_cars) ----
     R vx = R(0), vy = R(0);
-    if (has_path) {
+    if (v.has_path) {
         a.route_time[i] = rt + a.dt;
         // Both speed factors have the form log(d / den) / L on (stop, free]:
         //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den) (cached)
@@ -406,16 +493,16 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
         R f = r0;   // curvature factor without an obstacle, obstacle factor with one
         if (weigh) f = r0 * cos_(d_car / a.free_distance) + r1 * sin_(d_node / a.free_distance);  // models.py:41-66
         f = fabs(f);
-        vx = dx / d_node * a.speed_limit * f;
-        vy = dy / d_node * a.speed_limit * f;
+        vx = v.dx / d_node * a.speed_limit * f;
+        vy = v.dy / d_node * a.speed_limit * f;
         if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) & isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
             const bool acc = !r_t && (!c_t || d_car > a.stop_distance);
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
         }
-        if (crossed) {
+        if (v.crossed) {
             a.cursor[i] = cur + 1;
             // new head: the point we just steered to, or the destination once no usable route point is left
-            a.head_xy[i] = (cur + 1 >= eff && path_len >= 2) ? a.dest_xy[i] : t;
+            a.head_xy[i] = (cur + 1 >= eff && v.path_len >= 2) ? a.dest_xy[i] : mk2(v.tx, v.ty);
             if (cur + 1 < end) a.head_curv[i] = a.pt_curv[cur + 1];
         }
     } else if (cur != end) {
@@ -434,7 +521,10 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
     if (cn != c) a.cell[i] = cn;
-    if (!a.skip_insert) table_insert(rot.tab_next, cbase + cn, i);
+    if (!a.skip_insert) {
+        int32_t* tn = &a.cell_dyn[cbase + cn].w[2 * rot.tab_next_k];
+        table_insert(tn, i, cn == c ? sec_next : __ldcg(tn + 1));
+    }
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
@@ -447,20 +537,60 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     }
 }
 
+// Dependent-load waves of the plain (non-pipelined) form: (1) own state, coalesced; (2) the bin's dynamic record - table
+// entry, next-table entry, go word - one sector; (3) the candidate leader's position and, if the bin has a light, its
+// static record.  Everything else is arithmetic (the CSR / per-face arrays are only touched on the rare general paths).
+template <typename R, bool AUX, bool ENS>
+__device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& rot, const int i) {
+    using R2 = typename real2<R>::type;
+    // replica of this car (1 for a single simulation): offsets into the per-replica cell records and face states
+    const int rep = ENS ? i / a.cars_per_replica : 0;
+    const int cbase = rep * a.g.n_cells, fbase = rep * a.faces_per_replica;
+    // ---- wave 1: own state ----
+    const R2 p = rot.pos_in[i];
+    const int cur = a.cursor[i];
+    const int end = a.path_end[i];
+    const int eff = a.path_eff_end[i];
+    const int c = a.cell[i];
+    const R2 head = a.head_xy[i];
+    const R2 hc = a.head_curv[i];
+    const R rt = a.route_time[i];
+    // ---- wave 2: the bin's dynamic record (written by the previous step: bypass L1) ----
+    const CellDynT* dyn = a.cell_dyn + (cbase + c);
+    const int2 m = __ldcg(reinterpret_cast<const int2*>(&dyn->w[2 * rot.tab_cur_k]));
+    const int sec_next = __ldcg(&dyn->w[2 * rot.tab_next_k + 1]);
+    const uint32_t gw = (uint32_t)__ldcg(&dyn->w[TB2_DYN_GO + rot.go_k_cur]);
+    // ---- wave 3: candidate leader = first other car of the bin (navigation.py:438-442) ----
+    const int j = (m.x != i) ? m.x : m.y;
+    R2 o = mk2(R(0), R(0));
+    if (j != TB2_EMPTY) o = __ldcg(&rot.pos_in[j]);
+
+    const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff);
+    R d_car, d_light;
+    int lead;
+    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, [&]() { return a.cell_stat[c]; }, d_car, lead, d_light);
+    seg_move<R, AUX, ENS>(a, rot, i, rep, v, d_car, lead, d_light, hc, rt, cur, end, eff, c, sec_next);
+}
+
+__device__ __forceinline__ void clear_table(CellDynT* dyn, int k, int n_records, int first, int stride) {
+    for (int r = first; r < n_records; r += stride)
+        *reinterpret_cast<int2*>(&dyn[r].w[2 * k]) = make_int2(TB2_EMPTY, TB2_EMPTY);
+}
+
 // One launch per step: CTAs [0, car_blocks) take one car per thread, the trailing CTAs tick the lights.
 template <typename R, bool AUX, bool ENS>
 __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const __grid_constant__ StepArgsT<R> a) {
     if ((int)blockIdx.x >= a.car_blocks) {
         const int l = ((int)blockIdx.x - a.car_blocks) * TB2_BLOCK + (int)threadIdx.x;
-        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
-                         a.go_cur, a.go_next, a.t_cur, a.t_next);
+        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
+                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
         return;
     }
     const int i = (int)blockIdx.x * TB2_BLOCK + (int)threadIdx.x;
     // reset the table that the launch after next will fill
-    for (int k = i; k < 2 * a.g.n_cells * a.n_replicas; k += a.car_blocks * TB2_BLOCK) a.tab_clear[k] = TB2_EMPTY;
+    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, i, a.car_blocks * TB2_BLOCK);
     if (i >= a.n_cars) return;
-    const Rot<R> rot{a.pos_in, a.pos_out, a.tab_cur, a.tab_next, a.go_cur, a.step_index};
+    const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
     step_car<R, AUX, ENS>(a, rot, i);
 }
 
@@ -482,30 +612,30 @@ __global__ void __launch_bounds__(TB2_PERSIST_BLOCK, GRID ? 2 : 1)
 persistent_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ PersistArgsT<R> pa) {
     const int nthreads = (int)(gridDim.x * blockDim.x);
     const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    const int n_tab = 2 * a.g.n_cells * a.n_replicas;
+    const int n_rec = a.g.n_cells * a.n_replicas;
     const int n_tick = a.n_lights > 0 ? a.n_lights : 1;   // thread 0 advances the clock even without lights
     int cp = pa.cur_pos, ct = pa.cur_tab, cgo = pa.cur_go, ck = pa.cur_t;
     if (pa.order == TB2K_ORDER_LIGHTS_CARS) {               // L (C L) (C L) ... C
         for (int lg = gtid; lg < n_tick; lg += nthreads)
-            lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time, a.face_ptr,
-                             pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1]);
+            lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
+                             a.face_ptr, pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1], a.light_cellinfo, a.cell_dyn,
+                             cgo ^ 1);
         cgo ^= 1; ck ^= 1;
         step_barrier<GRID>();
     }
     for (int s = 0; s < pa.n_steps; ++s) {
         const bool tick = pa.order != TB2K_ORDER_LIGHTS_CARS || s < pa.n_steps - 1;
-        int32_t* tab_clear = pa.tab[(ct + 2) % 3];
-        for (int k = gtid; k < n_tab; k += nthreads) tab_clear[k] = TB2_EMPTY;
+        clear_table(a.cell_dyn, (ct + 2) % 3, n_rec, gtid, nthreads);
         if (gtid < a.n_cars) {
-            const Rot<R> rot{pa.pos[cp], pa.pos[cp ^ 1], reinterpret_cast<const int2*>(pa.tab[ct]), pa.tab[(ct + 1) % 3],
-                             pa.go[cgo], a.step_index + s};
+            const Rot<R> rot{pa.pos[cp], pa.pos[cp ^ 1], pa.go[cgo], ct, (ct + 1) % 3, cgo, a.step_index + s};
             if (pa.aux_last && s == pa.n_steps - 1) step_car<R, true, ENS>(a, rot, gtid);
             else step_car<R, false, ENS>(a, rot, gtid);
         }
         if (tick) {
             for (int lg = gtid; lg < n_tick; lg += nthreads)
-                lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.dt64, a.switch_time,
-                                 a.face_ptr, pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1]);
+                lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64,
+                                 a.switch_time, a.face_ptr, pa.go[cgo], pa.go[cgo ^ 1], pa.t[ck], pa.t[ck ^ 1],
+                                 a.light_cellinfo, a.cell_dyn, cgo ^ 1);
             cgo ^= 1; ck ^= 1;
         }
         cp ^= 1; ct = (ct + 1) % 3;
@@ -536,7 +666,8 @@ __global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgsT
                                                            const typename real2<R>::type* __restrict__ pt_curv,
                                                            typename real2<R>::type* head_xy,
                                                            typename real2<R>::type* head_curv, int32_t* cell,
-                                                           int32_t* cell_prev, int32_t* tab, int cars_per_replica) {
+                                                           int32_t* cell_prev, CellDynT* cell_dyn, int table_k,
+                                                           int cars_per_replica) {
     const int i = (int)blockIdx.x * 256 + (int)threadIdx.x;
     if (i >= n_cars) return;
     const int cur = cursor[i];
@@ -549,7 +680,8 @@ __global__ void __launch_bounds__(256) prepare_cars_kernel(int n_cars, GridArgsT
     const int cn = cell_of<R>(g, p.x, p.y);
     cell[i] = cn;
     cell_prev[i] = cn;
-    table_insert(tab, (i / cars_per_replica) * g.n_cells + cn, i);
+    int32_t* t = &cell_dyn[(size_t)(i / cars_per_replica) * g.n_cells + cn].w[2 * table_k];
+    table_insert(t, i, __ldcg(t + 1));
 }
 
 // prepare: unit vectors of the light faces (models.unit_vector, models.py:74-76)
@@ -563,28 +695,62 @@ __global__ void __launch_bounds__(256) prepare_faces_kernel(int n_faces, const t
     face_unit[f] = mk2(fv.x / nf, fv.y / nf);
 }
 
-// prepare: per-cell light records (CSR range + first light inline)
+// prepare: per-cell static light records (first light inline) + per-light cell info (static bits of the go word)
 template <typename R>
 __global__ void __launch_bounds__(256) prepare_cells_kernel(int n_cells, const int32_t* __restrict__ cell_light_ptr,
                                                             const int32_t* __restrict__ cell_light_idx,
                                                             const typename real2<R>::type* __restrict__ light_xy,
-                                                            const int32_t* __restrict__ face_ptr, CellLightsT<R>* out) {
+                                                            const int32_t* __restrict__ face_ptr,
+                                                            const typename real2<R>::type* __restrict__ face_unit,
+                                                            CellStatT<R>* out, int2* light_cellinfo) {
     const int c = (int)blockIdx.x * 256 + (int)threadIdx.x;
     if (c >= n_cells) return;
-    CellLightsT<R> r{};
+    CellStatT<R> r{};
     const int lb = cell_light_ptr[c], le = cell_light_ptr[c + 1];
-    int nl = le - lb, nf0 = 0;
-    r.lb = lb; r.fb0 = 0; r.xy0 = mk2(R(0), R(0));
-    if (nl > 0) {
-        const int l = cell_light_idx[lb];
-        r.xy0 = light_xy[l]; r.fb0 = face_ptr[l]; nf0 = face_ptr[l + 1] - face_ptr[l];
+    const int nl = le - lb;
+    r.xy0 = mk2(R(0), R(0));
+    for (int k = 0; k < 8; ++k) r.fu[k] = 0;
+    for (int q = lb; q < le; ++q) {
+        const int l = cell_light_idx[q];
+        const int fb = face_ptr[l], nf = face_ptr[l + 1] - fb;
+        if (q == lb) {
+            r.xy0 = light_xy[l];
+            for (int k = 0; k < nf && k < 4; ++k) {   // NaN units (zero-length face vector) quantise to 0: never anti-parallel
+                r.fu[2 * k] = (int16_t)__float2int_rn((float)face_unit[fb + k].x * 32767.0f);
+                r.fu[2 * k + 1] = (int16_t)__float2int_rn((float)face_unit[fb + k].y * 32767.0f);
+            }
+        }
+        const uint32_t hi = ((uint32_t)(nl < 65535 ? nl : 65535) << 16) | ((uint32_t)(nf < 255 ? nf : 255) << 8);
+        light_cellinfo[l] = make_int2(q == lb ? c : -1, (int)hi);
     }
-    r.counts = (nl & 0xffff) | (nf0 << 16);   // config_ok() bounds both below 2^15
     out[c] = r;
 }
 
+// all tables empty, no go words
+static __global__ void init_dyn_kernel(CellDynT* dyn, size_t n) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        int4* q = reinterpret_cast<int4*>(&dyn[k]);
+        q[0] = make_int4(TB2_EMPTY, TB2_EMPTY, TB2_EMPTY, TB2_EMPTY);
+        q[1] = make_int4(TB2_EMPTY, TB2_EMPTY, 0, 0);
+    }
+}
 static __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
+}
+// go words of the current face-state buffer, for the lights that are the first of their bin
+static __global__ void __launch_bounds__(256) rebuild_go_words_kernel(int n_lights_total, int lights_per_replica,
+                                                                      int faces_per_replica, int n_cells,
+                                                                      const int32_t* __restrict__ face_ptr,
+                                                                      const uint8_t* __restrict__ go_cur,
+                                                                      const int2* __restrict__ light_cellinfo,
+                                                                      CellDynT* cell_dyn, int go_k) {
+    const int lg = (int)blockIdx.x * 256 + (int)threadIdx.x;
+    if (lg >= n_lights_total) return;
+    const int rep = lg / lights_per_replica, l = lg - rep * lights_per_replica;
+    const int2 info = light_cellinfo[l];
+    if (info.x < 0) return;
+    const uint32_t mask = go_mask_of(go_cur + (size_t)rep * faces_per_replica, face_ptr[l], face_ptr[l + 1]);
+    cell_dyn[(size_t)rep * n_cells + info.x].w[TB2_DYN_GO + go_k] = (int32_t)((uint32_t)info.y | mask);
 }
 
 template <typename R>
@@ -648,19 +814,26 @@ cudaError_t launch_persistent_t(const StepArgsT<R>& a, const PersistArgsT<R>& pa
 
 template <typename R>
 void launch_prepare_t(const StepArgsT<R>& a, typename real2<R>::type* pt_curv, typename real2<R>::type* face_unit,
-                      int n_faces, int32_t* tab3, int cur_table, cudaStream_t stream) {
-    const size_t n = (size_t)6 * a.g.n_cells * a.n_replicas;
+                      int n_faces, cudaStream_t stream) {
+    const size_t n = (size_t)a.g.n_cells * a.n_replicas;
     const size_t blocks = (n + 255) / 256;
-    fill_i32_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(tab3, n, TB2_EMPTY);
+    init_dyn_kernel<<<(int)(blocks < 1184 ? (blocks ? blocks : 1) : 1184), 256, 0, stream>>>(a.cell_dyn, n);
     if (n_faces > 0) prepare_faces_kernel<R><<<(n_faces + 255) / 256, 256, 0, stream>>>(n_faces, a.face_vec, face_unit);
+    const int L = a.lights_per_replica > 0 && a.n_lights > 0 ? a.n_lights / a.n_replicas : 0;
+    if (L > 0) fill_i32_kernel<<<(2 * L + 255) / 256, 256, 0, stream>>>(reinterpret_cast<int32_t*>(a.light_cellinfo), (size_t)2 * L, -1);
     prepare_cells_kernel<R><<<(a.g.n_cells + 255) / 256, 256, 0, stream>>>(a.g.n_cells, a.cell_light_ptr, a.cell_light_idx,
-                                                                          a.light_xy, a.face_ptr, a.cell_lights);
+                                                                          a.light_xy, a.face_ptr, face_unit, a.cell_stat,
+                                                                          a.light_cellinfo);
+    if (a.n_lights > 0)
+        rebuild_go_words_kernel<<<(a.n_lights + 255) / 256, 256, 0, stream>>>(a.n_lights, a.lights_per_replica,
+                                                                               a.faces_per_replica, a.g.n_cells, a.face_ptr,
+                                                                               a.go_cur, a.light_cellinfo, a.cell_dyn, a.go_k_cur);
     if (a.n_cars > 0) {
         prepare_points_kernel<R><<<(a.n_cars + 127) / 128, 128, 0, stream>>>(a.n_cars, a.cursor, a.path_end, a.path_xy,
                                                                                pt_curv, a.stop_distance, a.free_distance);
         prepare_cars_kernel<R><<<(a.n_cars + 255) / 256, 256, 0, stream>>>(
             a.n_cars, a.g, a.pos_in, a.cursor, a.path_eff_end, a.dest_xy, a.path_xy, pt_curv, a.head_xy, a.head_curv, a.cell,
-            a.cell_prev, tab3 + (size_t)2 * a.g.n_cells * a.n_replicas * cur_table, a.cars_per_replica);
+            a.cell_prev, a.cell_dyn, a.tab_cur_k, a.cars_per_replica);
     }
 }
 
