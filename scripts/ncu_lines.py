@@ -13,9 +13,14 @@ for r in rows:
     if r and r[0] == "Line No": hdr = r; continue
     if hdr and len(r) > 8 and r[0] != "":
         lines.append(r)
+def _i(v):
+    try:
+        return int(v or 0)
+    except ValueError:
+        return 0
 si = hdr.index("# Samples"); ie = hdr.index("Instructions Executed"); te = hdr.index("Thread Instructions Executed")
-tot_i = sum(int(r[ie] or 0) for r in lines); tot_s = sum(int(r[si] or 0) for r in lines)
+tot_i = sum(_i(r[ie]) for r in lines); tot_s = sum(_i(r[si]) for r in lines)
 print("total warp-inst", tot_i, "samples", tot_s)
-for r in sorted(lines, key=lambda r: -int(r[ie] or 0))[:top]:
-    i = int(r[ie] or 0); t = int(r[te] or 0)
-    print(r[0].rjust(4), ("%5.1f%%" % (100.0 * i / tot_i)), ("%5.1f%%s" % (100.0 * int(r[si] or 0) / max(tot_s, 1))), ("act %4.1f" % (t / max(i, 1))), r[1].strip()[:110])
+for r in sorted(lines, key=lambda r: -_i(r[ie]))[:top]:
+    i = _i(r[ie]); t = _i(r[te])
+    print(r[0].rjust(4), ("%5.1f%%" % (100.0 * i / tot_i)), ("%5.1f%%s" % (100.0 * _i(r[si]) / max(tot_s, 1))), ("act %4.1f" % (t / max(i, 1))), r[1].strip()[:110])

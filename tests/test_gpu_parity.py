@@ -13,6 +13,10 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 FLOAT_RTOL = 1e-9
+# 1e9 car-steps: the kernel evaluates the speed factor as (log d - log den) * (1/L) and the heading with one reciprocal
+# (<= 4 ulp from the reference's expressions), so a position now and then rounds to the neighbouring fp64 value; a
+# follower's speed responds to that ulp with d(v)/d(x) ~ 70/s, i.e. ~1e-8 relative.  Still 100x inside north_star's 1e-5.
+FLOAT_RTOL_1E9_CAR_STEPS = 1e-7
 
 
 def _native():
@@ -197,7 +201,7 @@ def test_properties_at_bench_size():
         sim.step(dt, 250, 1)
         oracle.run(w_cpu, dt, 250, 1, threads=os.cpu_count() or 1)
         sim.download_world(w_gpu)
-        worst = max(worst, _compare_worlds(w_gpu, w_cpu, FLOAT_RTOL, "1M cars, %d steps" % (250 * (chunk + 1))))
+        worst = max(worst, _compare_worlds(w_gpu, w_cpu, FLOAT_RTOL_1E9_CAR_STEPS, "1M cars, %d steps" % (250 * (chunk + 1))))
     print("1M cars x 1000 steps vs oracle: discrete outputs bit-exact, worst float rel err %.2e" % worst)
 
 
@@ -262,6 +266,7 @@ def test_sort_neighbour_source_equals_atomic_table(replicas):
 
 @pytest.mark.parametrize("order", [0, 1])
 def test_persistent_cluster_kernel_equals_per_step_launches(order, monkeypatch):
+    monkeypatch.delenv("TB2_FORCE_PIPE", raising=False)   # (the forced-pipeline coverage pass disables this path)
     """Small worlds run a whole tb2_step batch in one launch (thread-block cluster + cluster barrier per step); it must
     be indistinguishable from one launch per step, for both call orders, odd and even batch lengths, with aux columns."""
     native = _native()

@@ -135,6 +135,9 @@ struct tb2_sim {
     int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
     bool go_dirty = false;          // TB2_FACE_GO was uploaded: the per-bin go words must be re-derived before the next step
+    bool allow_pipe = true;         // TB2_NO_PIPE=1: big worlds use the plain one-thread-per-car kernel (A/B testing)
+    bool force_pipe = false;        // TB2_FORCE_PIPE=1: every world goes through the pipelined kernel (test coverage)
+    int n_sms = 0;
     bool allow_persistent = true;   // TB2_NO_PERSISTENT=1 in the environment forces one launch per step (A/B testing)
     int64_t launches = 0, steps = 0;
     double log_free_over_stop = 0.0;
@@ -204,7 +207,8 @@ void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
     a->agent_car = c.agent_car; a->step_index = (int32_t)s->steps;
     a->speed_limit = (R)c.speed_limit; a->stop_distance = (R)c.stop_distance; a->free_distance = (R)c.free_distance;
     a->default_acceleration = (R)c.default_acceleration;
-    a->log_free_over_stop = (R)s->log_free_over_stop;
+    a->log_stop = (R)std::log(c.stop_distance);
+    a->inv_log_free_over_stop = (R)(1.0 / s->log_free_over_stop);
     a->vel = s->buf<R2>(B_VEL);
     a->route_time = s->buf<R>(B_ROUTE_TIME);
     a->cursor = s->buf<int32_t>(B_CURSOR);
@@ -275,6 +279,14 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
     a.dt64 = dt;
     a.tick = tick;
     a.write_aux = aux;
+    // big worlds (at least two tiles per resident CTA): the software-pipelined persistent kernel
+    a.pipe_ctas = 0;
+    if (s->allow_pipe && s->n_sms > 0) {
+        const int resident = s->n_sms * pipe_ctas_per_sm();
+        const int tiles = (a.n_cars + pipe_block_threads() - 1) / pipe_block_threads();
+        if (tiles >= 2 * resident) a.pipe_ctas = resident;
+        else if (s->force_pipe && tiles > 0) a.pipe_ctas = tiles < resident ? tiles : resident;
+    }
     a.skip_insert = s->cfg.neighbor_mode == TB2_NEIGHBOR_SORT;
     launch_step(a, stream);
     if (a.skip_insert)   // north_star's pipeline: radix sort by bin + segment heads -> the same table
@@ -345,6 +357,16 @@ int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_s
     s->n_cells = (cfg->nbx + 1) * (cfg->nby + 1);
     s->log_free_over_stop = std::log(cfg->free_distance / cfg->stop_distance);  // host libm, simulation.py:180
     if (const char* np = std::getenv("TB2_NO_PERSISTENT")) s->allow_persistent = !(np[0] == '1');
+    if (const char* np = std::getenv("TB2_NO_PIPE")) s->allow_pipe = !(np[0] == '1');
+    if (const char* np = std::getenv("TB2_FORCE_PIPE")) s->force_pipe = (np[0] == '1');
+    if (s->force_pipe) s->allow_persistent = false;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&s->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            s->n_sms = 0;
+        }
+    }
     if (arena_dev) {
         if (arena_bytes < s->lay.total) { delete s; return fail(TB2_ERR_INVALID, "arena too small (see tb2_arena_bytes)"); }
         if (reinterpret_cast<uintptr_t>(arena_dev) % kAlign) { delete s; return fail(TB2_ERR_INVALID, "arena must be 256-byte aligned"); }

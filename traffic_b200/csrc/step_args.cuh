@@ -57,9 +57,10 @@ struct StepArgsT {
     int32_t n_cars, n_lights, car_blocks, write_aux;   // n_cars / n_lights: totals over all replicas
     int32_t n_replicas, cars_per_replica, lights_per_replica, faces_per_replica;
     int32_t agent_car, step_index;
-    int32_t skip_insert, pad0;   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
+    int32_t skip_insert;
+    int32_t pipe_ctas;           // > 0: launch the software-pipelined persistent kernel with this many car CTAs   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
     R speed_limit, stop_distance, free_distance, default_acceleration;
-    R log_free_over_stop;  // host libm log(free/stop), simulation.py:180
+    R log_stop, inv_log_free_over_stop;  // host libm log(stop), 1/log(free/stop): simulation.obstacle_factor, simulation.py:180
     R dt;
     R origin_x, origin_y;  // float mode: absolute = stored + origin; 0 in double mode
     double dt64;           // lights always tick in fp64 (cars.py:130-133 is a round-off artefact, Appendix B-6)
@@ -123,6 +124,8 @@ using StepArgs64 = StepArgsT<double>;
 using StepArgs32 = StepArgsT<float>;
 
 int step_block_threads();
+int pipe_block_threads();
+int pipe_ctas_per_sm();
 void launch_step(const StepArgs64& a, cudaStream_t stream);
 void launch_step(const StepArgs32& a, cudaStream_t stream);
 int persistent_max_cars(int precision_f32);   // largest world the persistent (one launch per batch) kernels can take

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) lights_tick_kernel(int n_lights, int ligh
 }  // namespace
 
 int step_block_threads() { return TB2_BLOCK; }
+int pipe_block_threads() { return TB2_PIPE_BLOCK; }
+int pipe_ctas_per_sm() { return TB2_PIPE_MIN_BLOCKS; }
 
 void launch_step(const StepArgs64& a, cudaStream_t stream) { tb2k::launch_step_t<double>(a, stream); }
 

@@ -41,6 +41,13 @@
 #ifndef TB2_BLOCK
 #define TB2_BLOCK 128   // threads per CTA of the step kernel (cars per CTA)
 #endif
+#define TB2_PIPE_BLOCK 128         // threads per CTA of the pipelined big-world kernel (cars per tile)
+#ifndef TB2_PIPE_MIN_BLOCKS
+#define TB2_PIPE_MIN_BLOCKS 5      // resident CTAs per SM (96 registers per thread, ~25 KB of staging per CTA)
+#endif
+#ifndef TB2_PIPE_L2_AHEAD
+#define TB2_PIPE_L2_AHEAD 3        // own-state columns are bulk-prefetched into L2 this many tiles ahead
+#endif
 #define TB2_PERSIST_BLOCK 256      // threads per CTA of the persistent small-world kernel
 #define TB2_PERSIST_MAX_CTAS 16    // one thread-block cluster (16 needs the non-portable-size opt-in)
 #define TB2K_ORDER_LIGHTS_CARS 1
@@ -63,6 +70,8 @@ template <> struct K<float> {
 
 __device__ __forceinline__ double rsqrt_(double v) { return rsqrt(v); }
 __device__ __forceinline__ float rsqrt_(float v) { return rsqrtf(v); }
+__device__ __forceinline__ double rcp_(double v) { return __drcp_rn(v); }
+__device__ __forceinline__ float rcp_(float v) { return 1.0f / v; }
 __device__ __forceinline__ double log_(double v) { return log(v); }
 __device__ __forceinline__ float log_(float v) { return logf(v); }
 __device__ __forceinline__ double cos_(double v) { return cos(v); }
@@ -193,6 +202,38 @@ __device__ __forceinline__ bool on_axis(const Axis<double>& a, int kmin, double 
     }
     return on_axis_exact(a.start, a.stop, a.n, kmin, v);
 }
+// The same filter with everything that depends only on the axis hoisted out of the per-candidate test: sample spacing,
+// its reciprocal, and the tolerance taken at the axis START instead of at the candidate (|tol(v) - tol(start)| =
+// 1e-6 |v - start| is folded into the band).  One car tests up to four candidates coordinates per step (leader x/y, light
+// x/y) against the same two axes.
+struct AxisFilter {
+    float fs, inv_fs, nm1, tf0, epsc;
+    bool ok;
+};
+__device__ __forceinline__ AxisFilter axis_filter(const Axis<double>& a) {
+    AxisFilter f;
+    f.ok = a.n >= 2 && a.n < 100000;
+    const float fd = __double2float_rn(a.delta);
+    f.nm1 = (float)(a.n - 1);
+    f.fs = __fdividef(fd, f.nm1);
+    f.inv_fs = __fdividef(f.nm1, fd);
+    f.tf0 = __double2float_rn(1.0e-8 + 1.0e-6 * fabs(a.start));
+    f.epsc = __fmaf_rn(2.0e-6f, fabsf(fd), 2.5e-3f);
+    return f;
+}
+__device__ __forceinline__ bool on_axis(const Axis<double>& a, const AxisFilter& f, int kmin, double v) {
+    if (a.n - kmin <= 0) return false;
+    if (f.ok) {
+        const float w = __double2float_rn(v - a.start);
+        float k = rintf(w * f.inv_fs);
+        k = fminf(fmaxf(k, (float)kmin), f.nm1);              // NaN -> kmin
+        const float r = fabsf(__fmaf_rn(-k, f.fs, w));         // distance to the nearest sample with index in [kmin, n-1]
+        const float eps = __fmaf_rn(2.0e-6f, fabsf(w), f.epsc);
+        if (r + eps < f.tf0) return true;
+        if (r - eps > f.tf0) return false;
+    }
+    return on_axis_exact(a.start, a.stop, a.n, kmin, v);
+}
 // float mode: the fp32 distance decides (tolerance from the absolute coordinate)
 __device__ __forceinline__ bool on_axis(const Axis<float>& a, int kmin, float v, float origin) {
     if (a.n - kmin <= 0) return false;
@@ -220,8 +261,9 @@ __device__ __noinline__ R view_angle(typename real2<R>::type p0, typename real2<
 }
 
 // Curvature constants of the view whose head is polyline point q of a car whose polyline ends at `end`
-// (simulation.road_curvature_factor, simulation.py:135-164): returns (s, L) with
-//   s = stop*2*theta/pi and L = log(free/s), or s = 0 when the factor is identically 1 (theta isclose 0).
+// (simulation.road_curvature_factor, simulation.py:135-164): with s = stop*2*theta/pi the factor on (stop, free] is
+// log(d/s) / log(free/s); cached as (log s, 1/log(free/s)) so that the step evaluates (log d - log s) * inv_L - one
+// log, no division.  (0, 0) when the factor is identically 1 (theta isclose 0).
 template <typename R>
 __device__ __forceinline__ typename real2<R>::type curv_constants(const typename real2<R>::type* __restrict__ path_xy,
                                                                   int q, int end, R stop_d, R free_d) {
@@ -232,7 +274,7 @@ __device__ __forceinline__ typename real2<R>::type curv_constants(const typename
     else theta = R(0);  // models.get_angles returns False
     if (isclose_<R>(theta, R(0), R(1.0e-1), R(1.0e-8))) return mk2(R(0), R(0));
     const R s = stop_d * 2 * theta / K<R>::pi;
-    return mk2(s, log_(free_d / s));
+    return mk2(log_(s), R(1) / log_(free_d / s));
 }
 
 // models.determine_anti_parallel_vectors  (navigation.py:481-489, models.py:90-97).
@@ -414,22 +456,34 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
                                            const View<R>& v, int j, typename real2<R>::type o, uint32_t gw,
                                            LoadStat load_stat, R& d_car, int& lead, R& d_light) {
     const Axis<R> ax = axis_of<R>(v.x, v.tx, v.dx, v.nx), ay = axis_of<R>(v.y, v.ty, v.dy, v.ny);
+    const int nl = (int)(gw >> 16), nf0 = (int)((gw >> 8) & 0xffu);
     d_car = R(0);
     lead = -1;
-    if (v.spaces && j != TB2_EMPTY) {
-        if (on_axis(ax, 0, o.x, a.origin_x) && on_axis(ay, 0, o.y, a.origin_y)) {
+    d_light = R(0);
+    if (!(v.spaces && (j != TB2_EMPTY || nl))) return;
+    // membership of a coordinate in one of the two linspaces (filtered in double mode, plain fp32 in float mode)
+    [[maybe_unused]] AxisFilter ffx, ffy;
+    if constexpr (is_f64<R>) { ffx = axis_filter(ax); ffy = axis_filter(ay); }
+    auto on_x = [&](int kmin, R val) {
+        if constexpr (is_f64<R>) return on_axis(ax, ffx, kmin, val);
+        else return on_axis(ax, kmin, val, a.origin_x);
+    };
+    auto on_y = [&](int kmin, R val) {
+        if constexpr (is_f64<R>) return on_axis(ay, ffy, kmin, val);
+        else return on_axis(ay, kmin, val, a.origin_y);
+    };
+    if (j != TB2_EMPTY) {
+        if (on_x(0, o.x) && on_y(0, o.y)) {
             d_car = norm2<R>(o.x - v.x, o.y - v.y);
             if (d_car != R(0)) lead = j;
         }
     }
-    d_light = R(0);
-    const int nl = (int)(gw >> 16), nf0 = (int)((gw >> 8) & 0xffu);
-    if (v.spaces && nl) {
+    if (nl) {
         if (nf0 > 4) {
             d_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, v.tx, v.y, v.ty);
         } else {
             const CellStatT<R> st = load_stat();
-            if (on_axis(ax, 1, st.xy0.x, a.origin_x) && on_axis(ay, 1, st.xy0.y, a.origin_y)) {
+            if (on_x(1, st.xy0.x) && on_y(1, st.xy0.y)) {
                 // first light of the bin: faces from the static record (snorm16 units), go bits from the go word
                 const R cvx = st.xy0.x - v.x, cvy = st.xy0.y - v.y;
                 const float fx = (float)cvx, fy = (float)cvy;
@@ -467,10 +521,12 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     if (v.has_path) {
         a.route_time[i] = rt + a.dt;
         // Both speed factors have the form log(d / den) / L on (stop, free]:
-        //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den) (cached)
+        //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den)
         //   simulation.obstacle_factor       (simulation.py:167-186): den = stop,            L = log(free/stop)
-        // so they share one code path.  Pass 0 evaluates the factor the car actually uses (obstacle factor when it
-        // has an obstacle, curvature factor otherwise); pass 1 only runs for cars that blend both (models.weigh_factors).
+        // so they share one code path, evaluated as (log d - log den) * (1/L) with log den and 1/L cached per route
+        // point (curvature) or per simulation (obstacle): one log and no division per car, within 4 ulp of the
+        // reference's expression.  Pass 0 evaluates the factor the car actually uses (obstacle factor when it has an
+        // obstacle, curvature factor otherwise); pass 1 only runs for cars that blend both (models.weigh_factors).
         const bool c_t = d_car != R(0), r_t = d_light != R(0);  // Python truthiness (NaN truthy)
         const bool obs = c_t || r_t;
         const bool weigh = c_t && !r_t && d_car > d_node;      // simulation.py:120-126
@@ -479,13 +535,13 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
 #pragma unroll 1
         for (int it = 0; it < 2; ++it) {
             const bool as_obs = (it == 0) && obs;
-            const bool wanted = (it == 0) ? (obs || hc.x != R(0)) : (weigh && hc.x != R(0));
+            const bool wanted = (it == 0) ? (obs || hc.y != R(0)) : (weigh && hc.y != R(0));
             const R d = as_obs ? d_obs : d_node;
-            const R den = as_obs ? a.stop_distance : hc.x;
-            const R L = as_obs ? a.log_free_over_stop : hc.y;
+            const R log_den = as_obs ? a.log_stop : hc.x;
+            const R inv_L = as_obs ? a.inv_log_free_over_stop : hc.y;
             R r = R(1);
             if (wanted) {
-                if (a.stop_distance < d && d <= a.free_distance) r = log_(d / den) / L;
+                if (a.stop_distance < d && d <= a.free_distance) r = (log_(d) - log_den) * inv_L;
                 else if (as_obs && d <= a.stop_distance) r = R(0);
             }
             if (it == 0) r0 = r; else r1 = r;
@@ -493,8 +549,10 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         R f = r0;   // curvature factor without an obstacle, obstacle factor with one
         if (weigh) f = r0 * cos_(d_car / a.free_distance) + r1 * sin_(d_node / a.free_distance);  // models.py:41-66
         f = fabs(f);
-        vx = v.dx / d_node * a.speed_limit * f;
-        vy = v.dy / d_node * a.speed_limit * f;
+        // unit(target - pos) * speed * factor (simulation.py:54-58) with one reciprocal instead of two divisions (<= 1 ulp)
+        const R inv_d = rcp_(d_node);
+        vx = v.dx * inv_d * a.speed_limit * f;
+        vy = v.dy * inv_d * a.speed_limit * f;
         if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) & isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
             const bool acc = !r_t && (!c_t || d_car > a.stop_distance);
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
@@ -592,6 +650,177 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
     if (i >= a.n_cars) return;
     const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
     step_car<R, AUX, ENS>(a, rot, i);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Big worlds: the software-pipelined form of the step.  A persistent grid (TB2_PIPE_MIN_BLOCKS CTAs per SM) walks the
+// cars in tiles of TB2_PIPE_BLOCK; every thread keeps the operands of its NEXT tiles in flight with cp.async while it
+// computes the current one, so no segment ever waits for global memory:
+//
+//   group       contents (per thread)                                   issued                 consumed
+//   G1(k+2)     pos, head point, cursor/end/eff_end/bin of tile k+2      end of tile k          seg_view of tile k+2
+//   GL(k)       curvature constants, route_time of tile k                start of tile k        seg_move of tile k
+//   G2(k+1)     dynamic bin record of tile k+1 (table entry, next-table  after seg_detect(k)    end of tile k (-> G3)
+//               entry, go word) - address needs the bin id from G1(k+1)
+//   G3(k+1)     candidate leader position + static light record of       end of tile k          seg_detect of tile k+1
+//               tile k+1 - address needs the table entry from G2(k+1)
+//
+// The staged operands are thread-private slots in shared memory (structure of arrays, conflict-free), each thread waits
+// only for its own cp.async groups: no block-wide barrier anywhere.  ~200 bytes of shared memory per thread replace the
+// registers (and the occupancy) a load-everything-first kernel needs to cover three dependent memory waves.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem)), "l"(gmem), "n"(BYTES) : "memory");
+}
+// cp.async.bulk.prefetch.L2: one instruction pulls `bytes` contiguous bytes (16-byte granular) from HBM into L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, int bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename R>
+struct PipeSmemT {
+    using R2 = typename real2<R>::type;
+    R2 pos[2][TB2_PIPE_BLOCK];
+    R2 head[2][TB2_PIPE_BLOCK];
+    int32_t cur[2][TB2_PIPE_BLOCK], end[2][TB2_PIPE_BLOCK], eff[2][TB2_PIPE_BLOCK], cell[2][TB2_PIPE_BLOCK];
+    R2 hc[TB2_PIPE_BLOCK];
+    R rt[TB2_PIPE_BLOCK];
+    int2 m[2][TB2_PIPE_BLOCK];
+    int32_t sec[2][TB2_PIPE_BLOCK], gw[2][TB2_PIPE_BLOCK];
+    R2 cand[TB2_PIPE_BLOCK];
+    int4 st_lo[TB2_PIPE_BLOCK], st_hi[TB2_PIPE_BLOCK];   // CellStatT<R> in two 16-byte halves
+};
+
+template <typename R, bool AUX, bool ENS>
+__global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kernel(const __grid_constant__ StepArgsT<R> a) {
+    using R2 = typename real2<R>::type;
+    constexpr int B = TB2_PIPE_BLOCK;
+    __shared__ __align__(16) PipeSmemT<R> sm;
+    const int tid = (int)threadIdx.x;
+    if ((int)blockIdx.x >= a.pipe_ctas) {   // trailing CTAs: TrafficLights.update
+        const int l = ((int)blockIdx.x - a.pipe_ctas) * B + tid;
+        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
+                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
+        return;
+    }
+    const int stride = a.pipe_ctas * B;
+    // reset the table that the launch after next will fill
+    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
+
+    auto issue_early = [&](int ii, int s) {
+        if (ii < a.n_cars) {
+            cp_async<sizeof(R2)>(&sm.pos[s][tid], &a.pos_in[ii]);
+            cp_async<sizeof(R2)>(&sm.head[s][tid], &a.head_xy[ii]);
+            cp_async<4>(&sm.cur[s][tid], &a.cursor[ii]);
+            cp_async<4>(&sm.end[s][tid], &a.path_end[ii]);
+            cp_async<4>(&sm.eff[s][tid], &a.path_eff_end[ii]);
+            cp_async<4>(&sm.cell[s][tid], &a.cell[ii]);
+        }
+        cp_async_commit();
+    };
+    auto issue_late = [&](int ii) {
+        if (ii < a.n_cars) {
+            cp_async<sizeof(R2)>(&sm.hc[tid], &a.head_curv[ii]);
+            cp_async<sizeof(R)>(&sm.rt[tid], &a.route_time[ii]);
+        }
+        cp_async_commit();
+    };
+    auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
+        if (ii < a.n_cars) {
+            const int rep = ENS ? ii / a.cars_per_replica : 0;
+            const CellDynT* dyn = a.cell_dyn + (rep * a.g.n_cells + sm.cell[s][tid]);
+            cp_async<8>(&sm.m[s][tid], &dyn->w[2 * a.tab_cur_k]);
+            cp_async<4>(&sm.sec[s][tid], &dyn->w[2 * a.tab_next_k + 1]);
+            cp_async<4>(&sm.gw[s][tid], &dyn->w[TB2_DYN_GO + a.go_k_cur]);
+        }
+        cp_async_commit();
+    };
+    auto issue_cand = [&](int ii, int s) {    // needs G2 of that tile
+        if (ii < a.n_cars) {
+            const int2 m = sm.m[s][tid];
+            const int j = (m.x != ii) ? m.x : m.y;
+            if (j != TB2_EMPTY) cp_async<sizeof(R2)>(&sm.cand[tid], &a.pos_in[j]);
+            if (((uint32_t)sm.gw[s][tid]) >> 16) {
+                const char* st = reinterpret_cast<const char*>(&a.cell_stat[sm.cell[s][tid]]);
+                cp_async<16>(&sm.st_lo[tid], st);
+                cp_async<16>(&sm.st_hi[tid], st + 16);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // One thread per CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 with
+    // bulk prefetches (whole tiles only), so that every cp.async below is an L2 hit.
+    auto prefetch_tile_l2 = [&](int first) {
+        if (tid != 0 || first + B > a.n_cars) return;
+        bulk_prefetch_l2(&a.pos_in[first], B * (int)sizeof(R2));
+        bulk_prefetch_l2(&a.head_xy[first], B * (int)sizeof(R2));
+        bulk_prefetch_l2(&a.head_curv[first], B * (int)sizeof(R2));
+        bulk_prefetch_l2(&a.route_time[first], B * (int)sizeof(R));
+        bulk_prefetch_l2(&a.cursor[first], B * 4);
+        bulk_prefetch_l2(&a.path_end[first], B * 4);
+        bulk_prefetch_l2(&a.path_eff_end[first], B * 4);
+        bulk_prefetch_l2(&a.cell[first], B * 4);
+    };
+
+    int i = (int)blockIdx.x * B + tid;
+    if ((int)blockIdx.x * B >= a.n_cars) return;
+    // ---- prologue: bring tile 0 to the loop invariant.  cp.async groups complete in commit order and wait_group counts
+    // from the youngest, so groups are committed in the order the loop consumes them: pending = [G3(0), G1(1)] ----
+    for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
+    issue_early(i, 0);
+    cp_async_wait<0>();
+    issue_dyn(i, 0);
+    cp_async_wait<0>();
+    issue_cand(i, 0);
+    issue_early(i + stride, 1);
+    int s = 0;
+    for (int base = (int)blockIdx.x * B; base < a.n_cars; base += stride, i += stride, s ^= 1) {
+        const bool live = i < a.n_cars;
+        const int rep = ENS ? i / a.cars_per_replica : 0;
+        prefetch_tile_l2(base + TB2_PIPE_L2_AHEAD * stride);
+        issue_late(i);                      // pending: G3(k), G1(k+1), GL(k)
+        View<R> v;
+        int cur = 0, end = 0, eff = 0, c = 0;
+        if (live) {
+            cur = sm.cur[s][tid]; end = sm.end[s][tid]; eff = sm.eff[s][tid]; c = sm.cell[s][tid];
+            v = seg_view<R>(a, i, sm.pos[s][tid], sm.head[s][tid], cur, end, eff);
+        }
+        cp_async_wait<2>();                 // G3(k) landed
+        R d_car = R(0), d_light = R(0);
+        int lead = -1;
+        if (live) {
+            const int2 m = sm.m[s][tid];
+            const int j = (m.x != i) ? m.x : m.y;
+            seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, c, v, j, sm.cand[tid], (uint32_t)sm.gw[s][tid],
+                          [&]() {
+                              union { CellStatT<R> st; int4 q[2]; } u;
+                              u.q[0] = sm.st_lo[tid]; u.q[1] = sm.st_hi[tid];
+                              return u.st;
+                          },
+                          d_car, lead, d_light);
+        }
+        cp_async_wait<1>();                 // G1(k+1) landed
+        issue_dyn(i + stride, s ^ 1);       // pending: GL(k), G2(k+1)
+        cp_async_wait<1>();                 // GL(k) landed
+        if (live)
+            seg_move<R, AUX, ENS>(a, rot, i, rep, v, d_car, lead, d_light, sm.hc[tid], sm.rt[tid], cur, end, eff, c,
+                                  sm.sec[s][tid]);
+        cp_async_wait<0>();                 // G2(k+1) landed
+        issue_cand(i + stride, s ^ 1);
+        issue_early(i + 2 * stride, s);     // pending: G3(k+1), G1(k+2)
+    }
+    cp_async_wait<0>();
 }
 
 // Small worlds (<= 4096 cars): ALL steps of a tb2_step batch in ONE launch.  The CTAs form a single thread-block cluster
@@ -755,11 +984,24 @@ static __global__ void __launch_bounds__(256) rebuild_go_words_kernel(int n_ligh
 
 template <typename R>
 void launch_step_t(const StepArgsT<R>& a, cudaStream_t stream) {
+    const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
+    if (a.pipe_ctas > 0) {   // big world: persistent software-pipelined grid
+        const int lb = (a.n_lights + TB2_PIPE_BLOCK - 1) / TB2_PIPE_BLOCK;
+        const int light_blocks = a.tick ? (lb > 0 ? lb : 1) : 0;
+        const int grid = a.pipe_ctas + light_blocks;
+        if (ens) {
+            if (a.write_aux) pipe_kernel<R, true, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+            else pipe_kernel<R, false, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+        } else {
+            if (a.write_aux) pipe_kernel<R, true, false><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+            else pipe_kernel<R, false, false><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+        }
+        return;
+    }
     const int lb = (a.n_lights + TB2_BLOCK - 1) / TB2_BLOCK;
     const int light_blocks = a.tick ? (lb > 0 ? lb : 1) : 0;
     const int grid = a.car_blocks + light_blocks;
     if (grid <= 0) return;
-    const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
     if (ens) {
         if (a.write_aux) step_kernel<R, true, true><<<grid, TB2_BLOCK, 0, stream>>>(a);
         else step_kernel<R, false, true><<<grid, TB2_BLOCK, 0, stream>>>(a);
