@@ -41,7 +41,7 @@ enum Buf {
     B_POS0, B_POS1, B_VEL, B_ROUTE_TIME, B_CURSOR, B_PATH_END, B_PATH_EFF_END, B_PATH_XY, B_DEST_XY,
     B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_CELL_DYN, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
     B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV,
-    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_STAT, B_LIGHT_CELLINFO, B_FRAME_STAGE, B_GO_STAGE, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
+    B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_STAT, B_LIGHT_CELLINFO, B_LOG_TABLE, B_FRAME_STAGE, B_GO_STAGE, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
     B_SORT_VALS_OUT, B_SORT_TEMP, B_COUNT
 };
 
@@ -109,6 +109,7 @@ Layout make_layout(const tb2_config& c) {
     b[B_TRIP_TIME] = Rep * 8;
     b[B_CELL_STAT] = C * 32;
     b[B_LIGHT_CELLINFO] = L * 8;
+    b[B_LOG_TABLE] = 128 * 32;   // LogEntry[TB2_LOG_N]
     b[B_FRAME_STAGE] = N * 2 * R;   // snapshot of the positions / faces that a pipelined frame copy reads from
     b[B_GO_STAGE] = Rep * F;
     const bool sorted = c.neighbor_mode == TB2_NEIGHBOR_SORT;
@@ -199,6 +200,8 @@ void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
     a->g.ex0 = (R)(c.ex0 - ox); a->g.ex1 = (R)(c.ex1 - ox); a->g.exd = (R)c.exd;
     a->g.ey0 = (R)(c.ey0 - oy); a->g.ey1 = (R)(c.ey1 - oy); a->g.eyd = (R)c.eyd;
     a->g.inv_exd = (R)(1.0 / c.exd); a->g.inv_eyd = (R)(1.0 / c.eyd);
+    a->g.f_inv_exd = (float)(1.0 / c.exd); a->g.f_inv_eyd = (float)(1.0 / c.eyd);
+    a->g.f_nbx1 = (float)(c.nbx - 1); a->g.f_nby1 = (float)(c.nby - 1);
     a->origin_x = (R)ox; a->origin_y = (R)oy;
     a->n_replicas = c.n_replicas; a->cars_per_replica = c.n_cars > 0 ? c.n_cars : 1;
     a->lights_per_replica = c.n_lights > 0 ? c.n_lights : 1; a->faces_per_replica = c.n_faces;
@@ -207,6 +210,8 @@ void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
     a->agent_car = c.agent_car; a->step_index = (int32_t)s->steps;
     a->speed_limit = (R)c.speed_limit; a->stop_distance = (R)c.stop_distance; a->free_distance = (R)c.free_distance;
     a->default_acceleration = (R)c.default_acceleration;
+    a->log_table = s->buf<char>(B_LOG_TABLE);
+    a->log_scale = (R)(128.0 / (c.free_distance - c.stop_distance));
     a->log_stop = (R)std::log(c.stop_distance);
     a->inv_log_free_over_stop = (R)(1.0 / s->log_free_over_stop);
     a->vel = s->buf<R2>(B_VEL);
@@ -457,7 +462,7 @@ int tb2_prepare(tb2_sim* s, void* stream_) {
         fill_args<float>(s, &a);
         launch_prepare(a, s->buf<float2>(B_PT_CURV), s->buf<float2>(B_FACE_UNIT), s->cfg.n_faces, stream);
     }
-    s->launches += 2 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0) + (s->cfg.n_lights > 0 ? 2 : 0);
+    s->launches += 3 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0) + (s->cfg.n_lights > 0 ? 2 : 0);
     CU(cudaGetLastError());
     s->go_dirty = false;
     s->prepared = true;

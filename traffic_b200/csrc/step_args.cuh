@@ -19,6 +19,8 @@ struct GridArgsT {
     int32_t nbx, nby, ncx, n_cells;
     R ex0, ex1, exd, ey0, ey1, eyd;  // bin edges: e[k] = k==0 ? e0 : k==1 ? e1 : e0 + k*ed   (models.py:16)
     R inv_exd, inv_eyd;              // 1/ed, only used for the index estimate
+    float f_inv_exd, f_inv_eyd;      // the same in fp32 (filters)
+    float f_nbx1, f_nby1;            // (float)(nb - 1)
 };
 
 // Per-cell records.  Everything a car needs from its 200 m bin is addressable from the bin id alone and arrives in ONE
@@ -60,6 +62,8 @@ struct StepArgsT {
     int32_t skip_insert;
     int32_t pipe_ctas;           // > 0: launch the software-pipelined persistent kernel with this many car CTAs   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
     R speed_limit, stop_distance, free_distance, default_acceleration;
+    const void* log_table;   // LogEntry[TB2_LOG_N]: log over (stop, free] (see log_stop_free)
+    R log_scale;             // TB2_LOG_N / (free - stop)
     R log_stop, inv_log_free_over_stop;  // host libm log(stop), 1/log(free/stop): simulation.obstacle_factor, simulation.py:180
     R dt;
     R origin_x, origin_y;  // float mode: absolute = stored + origin; 0 in double mode

@@ -43,7 +43,7 @@
 #endif
 #define TB2_PIPE_BLOCK 128         // threads per CTA of the pipelined big-world kernel (cars per tile)
 #ifndef TB2_PIPE_MIN_BLOCKS
-#define TB2_PIPE_MIN_BLOCKS 5      // resident CTAs per SM (96 registers per thread, ~25 KB of staging per CTA)
+#define TB2_PIPE_MIN_BLOCKS 5      // resident CTAs per SM (96 registers per thread, no spills; ~36 KB of staging per CTA)
 #endif
 #ifndef TB2_PIPE_L2_AHEAD
 #define TB2_PIPE_L2_AHEAD 3        // own-state columns are bulk-prefetched into L2 this many tiles ahead
@@ -118,15 +118,16 @@ __device__ __forceinline__ int digitize_exact(double x, int nb, double e0, doubl
 // Filtered predicate: an fp32 estimate of the fractional bin index decides when x is at least 0.4 m (2e-3 bins) away
 // from every edge - the estimate's error is < 1e-4 bins for maps up to ~100 km - and the exact fp64 routine runs only
 // for positions inside that band (or outside the edge range, or non-finite).
-__device__ __forceinline__ int digitize_(double x, int nb, double e0, double e1, double d, double inv_d) {
-    const float fx = __double2float_rn(x - e0) * __double2float_rn(inv_d);
+__device__ __forceinline__ int digitize_(double x, int nb, double e0, double e1, double d, double inv_d, float f_inv_d,
+                                         float f_nb1) {
+    const float fx = __double2float_rn(x - e0) * f_inv_d;
     const float k = floorf(fx);
     const float fr = fx - k;
-    if (fr > 2.0e-3f && fr < 1.0f - 2.0e-3f && k >= 0.0f && k < (float)(nb - 1) && nb < 30000) return (int)k + 1;
+    if (fr > 2.0e-3f && fr < 1.0f - 2.0e-3f && k >= 0.0f && k < f_nb1 && nb < 30000) return (int)k + 1;
     return digitize_exact(x, nb, e0, e1, d, inv_d);
 }
 // float mode: closed form on the (uniform) local edges
-__device__ __forceinline__ int digitize_(float x, int nb, float e0, float, float, float inv_d) {
+__device__ __forceinline__ int digitize_(float x, int nb, float e0, float, float, float inv_d, float, float) {
     if (nb <= 0) return 0;
     if (isnan(x)) return nb;
     const float q = floorf((x - e0) * inv_d) + 1.0f;
@@ -134,7 +135,8 @@ __device__ __forceinline__ int digitize_(float x, int nb, float e0, float, float
 }
 template <typename R>
 __device__ __forceinline__ int cell_of(const GridArgsT<R>& g, R x, R y) {
-    return digitize_(y, g.nby, g.ey0, g.ey1, g.eyd, g.inv_eyd) * g.ncx + digitize_(x, g.nbx, g.ex0, g.ex1, g.exd, g.inv_exd);
+    return digitize_(y, g.nby, g.ey0, g.ey1, g.eyd, g.inv_eyd, g.f_inv_eyd, g.f_nby1) * g.ncx +
+           digitize_(x, g.nbx, g.ex0, g.ex1, g.exd, g.inv_exd, g.f_inv_exd, g.f_nbx1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -221,7 +223,8 @@ __device__ __forceinline__ AxisFilter axis_filter(const Axis<double>& a) {
     f.epsc = __fmaf_rn(2.0e-6f, fabsf(fd), 2.5e-3f);
     return f;
 }
-__device__ __forceinline__ bool on_axis(const Axis<double>& a, const AxisFilter& f, int kmin, double v) {
+template <typename StopFn>
+__device__ __forceinline__ bool on_axis(const Axis<double>& a, const AxisFilter& f, int kmin, double v, StopFn stop) {
     if (a.n - kmin <= 0) return false;
     if (f.ok) {
         const float w = __double2float_rn(v - a.start);
@@ -232,7 +235,7 @@ __device__ __forceinline__ bool on_axis(const Axis<double>& a, const AxisFilter&
         if (r + eps < f.tf0) return true;
         if (r - eps > f.tf0) return false;
     }
-    return on_axis_exact(a.start, a.stop, a.n, kmin, v);
+    return on_axis_exact(a.start, stop(), a.n, kmin, v);   // the linspace end point is only needed here: fetched lazily
 }
 // float mode: the fp32 distance decides (tolerance from the absolute coordinate)
 __device__ __forceinline__ bool on_axis(const Axis<float>& a, int kmin, float v, float origin) {
@@ -411,35 +414,50 @@ struct Rot {
 // ---------------------------------------------------------------------------------------------------------------
 template <typename R>
 struct View {
-    R x, y, tx, ty, dx, dy, d_node;
+    R x, y, dx, dy, d_node;   // (the target itself is re-fetched by the rare paths that need it: fewer live registers)
     int nx, ny;          // int(|dx|), int(|dy|): lengths of the two linspaces
     bool has_path, crossed, spaces;
     int path_len;
 };
 
+// FrontView.crossed_node_event (navigation.py:91-111): tolerance relative to the car's ABSOLUTE coordinate
 template <typename R>
-__device__ __forceinline__ View<R> seg_view(const StepArgsT<R>& a, int i, typename real2<R>::type p,
-                                            typename real2<R>::type head, int cur, int end, int eff) {
-    using R2 = typename real2<R>::type;
+__device__ __forceinline__ bool view_crossed(const StepArgsT<R>& a, typename real2<R>::type p, typename real2<R>::type head,
+                                             int cur, int eff) {
+    return (cur < eff) & isclose_abs<R>(head.x, p.x, p.x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
+           isclose_abs<R>(head.y, p.y, p.y + a.origin_y, R(1.0e-5), R(1.0e-8));
+}
+// where a car that crosses its path head steers next (FrontView.upcoming_node_position, navigation.py:73-89): the next
+// route point, or the destination node when the head was the last one
+template <typename R>
+__device__ __forceinline__ const typename real2<R>::type* crossing_target(const StepArgsT<R>& a, int i, int cur, int end) {
+    return (end - cur < 2) ? &a.dest_xy[i] : &a.path_xy[cur + 1];
+}
+// t: the target - the cached head point (head_xy holds the destination once the route is exhausted, written by seg_move /
+// prepare, so a parked car needs no extra load), or *crossing_target() on a crossing step
+template <typename R>
+__device__ __forceinline__ View<R> view_build(const StepArgsT<R>& a, typename real2<R>::type p, typename real2<R>::type t,
+                                              int cur, int end, int eff, bool crossed) {
     View<R> v;
     v.x = p.x; v.y = p.y;
     v.has_path = cur < eff;
     v.path_len = v.has_path ? end - cur : 0;
-    // FrontView.crossed_node_event (navigation.py:91-111): tolerance relative to the car's ABSOLUTE coordinate
-    v.crossed = v.has_path & isclose_abs<R>(head.x, v.x, v.x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
-                isclose_abs<R>(head.y, v.y, v.y + a.origin_y, R(1.0e-5), R(1.0e-8));
-    // target (FrontView.upcoming_node_position, navigation.py:73-89).  head_xy holds the destination once the route is
-    // exhausted (written by seg_move / prepare), so a parked car needs no extra load; only the step that crosses the
-    // last route point fetches dest_xy, and a crossing step fetches the next route point.
-    R2 t = head;
-    if (v.crossed) t = (v.path_len < 2) ? a.dest_xy[i] : a.path_xy[cur + 1];
-    v.tx = t.x; v.ty = t.y;
+    v.crossed = crossed;
     v.dx = t.x - v.x; v.dy = t.y - v.y;
     v.d_node = norm2<R>(v.dx, v.dy);
-    const Axis<R> ax = make_axis<R>(v.x, v.tx), ay = make_axis<R>(v.y, v.ty);
+    const Axis<R> ax = make_axis<R>(v.x, t.x), ay = make_axis<R>(v.y, t.y);
     v.nx = ax.n; v.ny = ay.n;
     v.spaces = axis_any<R>(ax, a.origin_x) && axis_any<R>(ay, a.origin_y);
     return v;
+}
+template <typename R>
+__device__ __forceinline__ View<R> seg_view(const StepArgsT<R>& a, int i, typename real2<R>::type p,
+                                            typename real2<R>::type head, int cur, int end, int eff,
+                                            typename real2<R>::type& t) {
+    const bool crossed = view_crossed<R>(a, p, head, cur, eff);
+    t = head;
+    if (crossed) t = *crossing_target<R>(a, i, cur, end);
+    return view_build<R>(a, p, t, cur, end, eff, crossed);
 }
 
 template <typename R>
@@ -451,11 +469,12 @@ __device__ __forceinline__ Axis<R> axis_of(R start, R stop, R delta, int n) {
 
 // navigation.car_obstacles (navigation.py:422-456) against candidate j at position o, then navigation.light_obstacles
 // (navigation.py:459-498) for a bin whose go word is gw; load_stat() yields the bin's static light record.
-template <typename R, typename LoadStat>
+// target(): the car's target point (only the exact / general fall-backs ask for it)
+template <typename R, typename LoadStat, typename Target>
 __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fbase, int c,
                                            const View<R>& v, int j, typename real2<R>::type o, uint32_t gw,
-                                           LoadStat load_stat, R& d_car, int& lead, R& d_light) {
-    const Axis<R> ax = axis_of<R>(v.x, v.tx, v.dx, v.nx), ay = axis_of<R>(v.y, v.ty, v.dy, v.ny);
+                                           LoadStat load_stat, Target target, R& d_car, int& lead, R& d_light) {
+    const Axis<R> ax = axis_of<R>(v.x, R(0), v.dx, v.nx), ay = axis_of<R>(v.y, R(0), v.dy, v.ny);
     const int nl = (int)(gw >> 16), nf0 = (int)((gw >> 8) & 0xffu);
     d_car = R(0);
     lead = -1;
@@ -465,11 +484,11 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
     [[maybe_unused]] AxisFilter ffx, ffy;
     if constexpr (is_f64<R>) { ffx = axis_filter(ax); ffy = axis_filter(ay); }
     auto on_x = [&](int kmin, R val) {
-        if constexpr (is_f64<R>) return on_axis(ax, ffx, kmin, val);
+        if constexpr (is_f64<R>) return on_axis(ax, ffx, kmin, val, [&]() { return target().x; });
         else return on_axis(ax, kmin, val, a.origin_x);
     };
     auto on_y = [&](int kmin, R val) {
-        if constexpr (is_f64<R>) return on_axis(ay, ffy, kmin, val);
+        if constexpr (is_f64<R>) return on_axis(ay, ffy, kmin, val, [&]() { return target().y; });
         else return on_axis(ay, kmin, val, a.origin_y);
     };
     if (j != TB2_EMPTY) {
@@ -480,7 +499,8 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
     }
     if (nl) {
         if (nf0 > 4) {
-            d_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, v.tx, v.y, v.ty);
+            const typename real2<R>::type t = target();
+            d_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
         } else {
             const CellStatT<R> st = load_stat();
             if (on_x(1, st.xy0.x) && on_y(1, st.xy0.y)) {
@@ -502,17 +522,47 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
                 }
                 if (!found && band) found = first_light_band_exact<R>(a, c, band, cvx, cvy);
                 if (found) d_light = norm2<R>(cvx, cvy);
-                else if (nl > 1) d_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, v.tx, v.y, v.ty);
+                else if (nl > 1) {
+                    const typename real2<R>::type t = target();
+                    d_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, t.x, v.y, t.y);
+                }
                 else d_light = -R(0);   // lights exhausted -> None
             }
         }
     }
 }
 
-template <typename R, bool AUX, bool ENS>
-__device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& rot, int i, int rep, const View<R>& v,
-                                         R d_car, int lead, R d_light, typename real2<R>::type hc, R rt, int cur, int end,
-                                         int eff, int c, int sec_next) {
+// log(d) for d in (stop, free] - the only interval on which either speed factor needs a logarithm - from a 128-entry
+// table of (c_k, 1/c_k, log c_k) over equal sub-intervals: log d = log c_k + log1p(u), u = (d - c_k)/c_k, |u| < 8e-3,
+// degree-7 series.  <= 2 ulp from a correctly rounded log, ~15 instructions instead of libdevice's ~100.
+#define TB2_LOG_N 128
+struct alignas(32) LogEntry { double c, inv_c, log_c, pad; };
+__device__ __forceinline__ double log_stop_free(const LogEntry* __restrict__ tab, double d, double stop, double scale) {
+    int k = (int)((d - stop) * scale);
+    k = k < 0 ? 0 : (k > TB2_LOG_N - 1 ? TB2_LOG_N - 1 : k);
+    const double2 ci = *reinterpret_cast<const double2*>(&tab[k].c);
+    const double lc = tab[k].log_c;
+    const double u = (d - ci.x) * ci.y;
+    double p = 1.0 / 7.0;
+    p = fma(p, u, -1.0 / 6.0);
+    p = fma(p, u, 1.0 / 5.0);
+    p = fma(p, u, -1.0 / 4.0);
+    p = fma(p, u, 1.0 / 3.0);
+    p = fma(p, u, -0.5);
+    p = fma(p, u, 1.0);
+    return fma(u, p, lc);
+}
+__device__ __forceinline__ float log_stop_free(const LogEntry*, float d, float, float) { return logf(d); }
+
+// next_curv(): curvature constants of the route point after the head (pt_curv[cur + 1]); insert(t, i, sec): table
+// insertion policy (immediate, or deferred by the pipelined kernel).
+// route(): (cursor, path_end, path_eff_end) of the car and target(): its target point - only the crossing / parking
+// branches ask for them.
+template <typename R, bool AUX, bool ENS, typename Route, typename Target, typename NextCurv, typename Insert>
+__device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& rot, const LogEntry* __restrict__ logtab, int i,
+                                         int rep, const View<R>& v, R d_car, int lead, R d_light,
+                                         typename real2<R>::type hc, R rt, int c, int sec_next, Route route, Target target,
+                                         NextCurv next_curv, Insert insert) {
     using R2 = typename real2<R>::type;
     const int cbase = rep * a.g.n_cells, ibase = rep * a.cars_per_replica;
     const R x = v.x, y = v.y, d_node = v.d_node;
@@ -541,7 +591,8 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
             const R inv_L = as_obs ? a.inv_log_free_over_stop : hc.y;
             R r = R(1);
             if (wanted) {
-                if (a.stop_distance < d && d <= a.free_distance) r = (log_(d) - log_den) * inv_L;
+                if (a.stop_distance < d && d <= a.free_distance)
+                    r = (log_stop_free(logtab, d, a.stop_distance, a.log_scale) - log_den) * inv_L;
                 else if (as_obs && d <= a.stop_distance) r = R(0);
             }
             if (it == 0) r0 = r; else r1 = r;
@@ -558,13 +609,15 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
         }
         if (v.crossed) {
-            a.cursor[i] = cur + 1;
+            const int3 q = route();   // (cur, end, eff)
+            a.cursor[i] = q.x + 1;
             // new head: the point we just steered to, or the destination once no usable route point is left
-            a.head_xy[i] = (cur + 1 >= eff && v.path_len >= 2) ? a.dest_xy[i] : mk2(v.tx, v.ty);
-            if (cur + 1 < end) a.head_curv[i] = a.pt_curv[cur + 1];
+            a.head_xy[i] = (q.x + 1 >= q.z && v.path_len >= 2) ? a.dest_xy[i] : target();
+            if (q.x + 1 < q.y) a.head_curv[i] = next_curv();
         }
-    } else if (cur != end) {
-        a.cursor[i] = end;  // path becomes []
+    } else {
+        const int3 q = route();
+        if (q.x != q.y) a.cursor[i] = q.y;  // path becomes []
     }
     const R xn = x + vx * a.dt, yn = y + vy * a.dt;  // cars.py:89-90
     rot.pos_out[i] = mk2(xn, yn);
@@ -579,10 +632,8 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
     if (cn != c) a.cell[i] = cn;
-    if (!a.skip_insert) {
-        int32_t* tn = &a.cell_dyn[cbase + cn].w[2 * rot.tab_next_k];
-        table_insert(tn, i, cn == c ? sec_next : __ldcg(tn + 1));
-    }
+    // (a car that changed bin has no prefetched entry of its new bin: it simply takes the atomics, ~1 % of the cars)
+    if (!a.skip_insert) insert(&a.cell_dyn[cbase + cn].w[2 * rot.tab_next_k], i, cn == c ? sec_next : TB2_EMPTY);
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
@@ -599,7 +650,8 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
 // entry, next-table entry, go word - one sector; (3) the candidate leader's position and, if the bin has a light, its
 // static record.  Everything else is arithmetic (the CSR / per-face arrays are only touched on the rare general paths).
 template <typename R, bool AUX, bool ENS>
-__device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& rot, const int i) {
+__device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& rot, const LogEntry* __restrict__ logtab,
+                                         const int i) {
     using R2 = typename real2<R>::type;
     // replica of this car (1 for a single simulation): offsets into the per-replica cell records and face states
     const int rep = ENS ? i / a.cars_per_replica : 0;
@@ -623,11 +675,23 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     R2 o = mk2(R(0), R(0));
     if (j != TB2_EMPTY) o = __ldcg(&rot.pos_in[j]);
 
-    const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff);
+    R2 t;
+    const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff, t);
     R d_car, d_light;
     int lead;
-    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, [&]() { return a.cell_stat[c]; }, d_car, lead, d_light);
-    seg_move<R, AUX, ENS>(a, rot, i, rep, v, d_car, lead, d_light, hc, rt, cur, end, eff, c, sec_next);
+    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, [&]() { return a.cell_stat[c]; }, [&]() { return t; }, d_car, lead,
+                  d_light);
+    seg_move<R, AUX, ENS>(a, rot, logtab, i, rep, v, d_car, lead, d_light, hc, rt, c, sec_next,
+                          [&]() { return make_int3(cur, end, eff); }, [&]() { return t; },
+                          [&]() { return a.pt_curv[cur + 1]; },
+                          [](int32_t* t, int ii, int sec) { table_insert(t, ii, sec); });
+}
+
+// every CTA keeps the (stop, free] log table in shared memory; the caller synchronises the CTA afterwards
+__device__ __forceinline__ void load_log_table(LogEntry* dst, const LogEntry* __restrict__ src) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (int k = (int)threadIdx.x; k < 2 * TB2_LOG_N; k += (int)blockDim.x) d4[k] = s4[k];
 }
 
 __device__ __forceinline__ void clear_table(CellDynT* dyn, int k, int n_records, int first, int stride) {
@@ -644,12 +708,13 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
                          a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
         return;
     }
+    const LogEntry* logtab = reinterpret_cast<const LogEntry*>(a.log_table);   // 4 KB, L1-resident
     const int i = (int)blockIdx.x * TB2_BLOCK + (int)threadIdx.x;
     // reset the table that the launch after next will fill
     clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, i, a.car_blocks * TB2_BLOCK);
     if (i >= a.n_cars) return;
     const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
-    step_car<R, AUX, ENS>(a, rot, i);
+    step_car<R, AUX, ENS>(a, rot, logtab, i);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -698,6 +763,10 @@ struct PipeSmemT {
     int32_t sec[2][TB2_PIPE_BLOCK], gw[2][TB2_PIPE_BLOCK];
     R2 cand[TB2_PIPE_BLOCK];
     int4 st_lo[TB2_PIPE_BLOCK], st_hi[TB2_PIPE_BLOCK];   // CellStatT<R> in two 16-byte halves
+    R2 tgt[2][TB2_PIPE_BLOCK];     // crossing step: the next target (next route point / destination)
+    R2 ncurv[TB2_PIPE_BLOCK];      // crossing step: curvature constants of the next route point
+    int32_t crossed[TB2_PIPE_BLOCK];
+    LogEntry logtab[TB2_LOG_N];
 };
 
 template <typename R, bool AUX, bool ENS>
@@ -713,8 +782,6 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
         return;
     }
     const int stride = a.pipe_ctas * B;
-    // reset the table that the launch after next will fill
-    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
     const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
 
     auto issue_early = [&](int ii, int s) {
@@ -742,6 +809,11 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
             cp_async<8>(&sm.m[s][tid], &dyn->w[2 * a.tab_cur_k]);
             cp_async<4>(&sm.sec[s][tid], &dyn->w[2 * a.tab_next_k + 1]);
             cp_async<4>(&sm.gw[s][tid], &dyn->w[TB2_DYN_GO + a.go_k_cur]);
+            // a car that crosses its path head this step (~1.5 %) steers to the next route point: fetch it now
+            const int cur = sm.cur[s][tid];
+            const bool crossed = view_crossed<R>(a, sm.pos[s][tid], sm.head[s][tid], cur, sm.eff[s][tid]);
+            sm.crossed[tid] = crossed;
+            if (crossed) cp_async<sizeof(R2)>(&sm.tgt[s][tid], crossing_target<R>(a, ii, cur, sm.end[s][tid]));
         }
         cp_async_commit();
     };
@@ -754,6 +826,10 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
                 const char* st = reinterpret_cast<const char*>(&a.cell_stat[sm.cell[s][tid]]);
                 cp_async<16>(&sm.st_lo[tid], st);
                 cp_async<16>(&sm.st_hi[tid], st + 16);
+            }
+            if (sm.crossed[tid]) {
+                const int cur = sm.cur[s][tid];
+                if (cur + 1 < sm.end[s][tid]) cp_async<sizeof(R2)>(&sm.ncurv[tid], &a.pt_curv[cur + 1]);
             }
         }
         cp_async_commit();
@@ -774,52 +850,76 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
     };
 
     int i = (int)blockIdx.x * B + tid;
-    if ((int)blockIdx.x * B >= a.n_cars) return;
     // ---- prologue: bring tile 0 to the loop invariant.  cp.async groups complete in commit order and wait_group counts
-    // from the youngest, so groups are committed in the order the loop consumes them: pending = [G3(0), G1(1)] ----
-    for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
+    // from the youngest, so groups are committed in the order the loop consumes them: pending = [G3(0), G1(1)].
+    // The first tile's operands are requested before anything else; the log table and the reset of the table that the
+    // launch after next will fill ride in the shadow of that first HBM round trip. ----
     issue_early(i, 0);
+    for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
+    load_log_table(sm.logtab, reinterpret_cast<const LogEntry*>(a.log_table));
+    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    __syncthreads();
     cp_async_wait<0>();
     issue_dyn(i, 0);
     cp_async_wait<0>();
     issue_cand(i, 0);
     issue_early(i + stride, 1);
+    // table insertion of the previous tile, second half: the atomicMin that returned `pend_old` is consumed one tile later
+    int pend_rec = -1, pend_old = 0;   // record index of the bin, value the first atomicMin returned
+    auto finish_insert = [&](int ii) {
+        if (pend_rec < 0) return;
+        const int loser = pend_old > ii ? pend_old : ii;   // whoever is not the bin minimum competes for second place
+        if (loser != TB2_EMPTY) atomicMin(&a.cell_dyn[pend_rec].w[2 * a.tab_next_k + 1], loser);
+        pend_rec = -1;
+    };
     int s = 0;
-    for (int base = (int)blockIdx.x * B; base < a.n_cars; base += stride, i += stride, s ^= 1) {
+    for (; i - tid < a.n_cars; i += stride, s ^= 1) {
         const bool live = i < a.n_cars;
         const int rep = ENS ? i / a.cars_per_replica : 0;
-        prefetch_tile_l2(base + TB2_PIPE_L2_AHEAD * stride);
+        prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
         issue_late(i);                      // pending: G3(k), G1(k+1), GL(k)
-        View<R> v;
-        int cur = 0, end = 0, eff = 0, c = 0;
+        View<R> v{};
+        // the staged copies stay in shared memory; whoever needs one of them again re-reads it (LDS) instead of keeping
+        // it in a register across the fp64 sections
+        auto target = [&]() { return v.crossed ? sm.tgt[s][tid] : sm.head[s][tid]; };
+        auto route = [&]() { return make_int3(sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid]); };
         if (live) {
-            cur = sm.cur[s][tid]; end = sm.end[s][tid]; eff = sm.eff[s][tid]; c = sm.cell[s][tid];
-            v = seg_view<R>(a, i, sm.pos[s][tid], sm.head[s][tid], cur, end, eff);
+            const bool crossed = sm.crossed[tid] != 0;
+            v = view_build<R>(a, sm.pos[s][tid], crossed ? sm.tgt[s][tid] : sm.head[s][tid], sm.cur[s][tid], sm.end[s][tid],
+                              sm.eff[s][tid], crossed);
         }
+        finish_insert(i - stride);
         cp_async_wait<2>();                 // G3(k) landed
         R d_car = R(0), d_light = R(0);
         int lead = -1;
         if (live) {
             const int2 m = sm.m[s][tid];
             const int j = (m.x != i) ? m.x : m.y;
-            seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, c, v, j, sm.cand[tid], (uint32_t)sm.gw[s][tid],
+            seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
+                          (uint32_t)sm.gw[s][tid],
                           [&]() {
                               union { CellStatT<R> st; int4 q[2]; } u;
                               u.q[0] = sm.st_lo[tid]; u.q[1] = sm.st_hi[tid];
                               return u.st;
                           },
-                          d_car, lead, d_light);
+                          target, d_car, lead, d_light);
         }
         cp_async_wait<1>();                 // G1(k+1) landed
         issue_dyn(i + stride, s ^ 1);       // pending: GL(k), G2(k+1)
         cp_async_wait<1>();                 // GL(k) landed
         if (live)
-            seg_move<R, AUX, ENS>(a, rot, i, rep, v, d_car, lead, d_light, sm.hc[tid], sm.rt[tid], cur, end, eff, c,
-                                  sm.sec[s][tid]);
+            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, sm.hc[tid], sm.rt[tid],
+                                  sm.cell[s][tid], sm.sec[s][tid], route, target, [&]() { return sm.ncurv[tid]; },
+                                  [&](int32_t* t, int ii, int sec) {
+                                      if (ii > sec) return;
+                                      pend_old = atomicMin(t, ii);
+                                      pend_rec = (int)((reinterpret_cast<CellDynT*>(t - 2 * a.tab_next_k)) - a.cell_dyn);
+                                  });
         cp_async_wait<0>();                 // G2(k+1) landed
         issue_cand(i + stride, s ^ 1);
         issue_early(i + 2 * stride, s);     // pending: G3(k+1), G1(k+2)
     }
+    finish_insert(i - stride);
     cp_async_wait<0>();
 }
 
@@ -844,6 +944,9 @@ persistent_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant_
     const int n_rec = a.g.n_cells * a.n_replicas;
     const int n_tick = a.n_lights > 0 ? a.n_lights : 1;   // thread 0 advances the clock even without lights
     int cp = pa.cur_pos, ct = pa.cur_tab, cgo = pa.cur_go, ck = pa.cur_t;
+    __shared__ LogEntry logtab[TB2_LOG_N];
+    load_log_table(logtab, reinterpret_cast<const LogEntry*>(a.log_table));
+    __syncthreads();
     if (pa.order == TB2K_ORDER_LIGHTS_CARS) {               // L (C L) (C L) ... C
         for (int lg = gtid; lg < n_tick; lg += nthreads)
             lights_tick_body(lg, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
@@ -857,8 +960,8 @@ persistent_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant_
         clear_table(a.cell_dyn, (ct + 2) % 3, n_rec, gtid, nthreads);
         if (gtid < a.n_cars) {
             const Rot<R> rot{pa.pos[cp], pa.pos[cp ^ 1], pa.go[cgo], ct, (ct + 1) % 3, cgo, a.step_index + s};
-            if (pa.aux_last && s == pa.n_steps - 1) step_car<R, true, ENS>(a, rot, gtid);
-            else step_car<R, false, ENS>(a, rot, gtid);
+            if (pa.aux_last && s == pa.n_steps - 1) step_car<R, true, ENS>(a, rot, logtab, gtid);
+            else step_car<R, false, ENS>(a, rot, logtab, gtid);
         }
         if (tick) {
             for (int lg = gtid; lg < n_tick; lg += nthreads)
@@ -955,6 +1058,18 @@ __global__ void __launch_bounds__(256) prepare_cells_kernel(int n_cells, const i
     out[c] = r;
 }
 
+// (stop, free] log table (see log_stop_free)
+static __global__ void build_log_table_kernel(LogEntry* tab, double stop, double free_d) {
+    const int k = (int)threadIdx.x;
+    if (k >= TB2_LOG_N) return;
+    const double w = (free_d - stop) / (double)TB2_LOG_N;
+    LogEntry e;
+    e.c = stop + ((double)k + 0.5) * w;
+    e.inv_c = 1.0 / e.c;
+    e.log_c = log(e.c);
+    e.pad = 0.0;
+    tab[k] = e;
+}
 // all tables empty, no go words
 static __global__ void init_dyn_kernel(CellDynT* dyn, size_t n) {
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
@@ -1060,6 +1175,8 @@ void launch_prepare_t(const StepArgsT<R>& a, typename real2<R>::type* pt_curv, t
     const size_t n = (size_t)a.g.n_cells * a.n_replicas;
     const size_t blocks = (n + 255) / 256;
     init_dyn_kernel<<<(int)(blocks < 1184 ? (blocks ? blocks : 1) : 1184), 256, 0, stream>>>(a.cell_dyn, n);
+    build_log_table_kernel<<<1, TB2_LOG_N, 0, stream>>>(reinterpret_cast<LogEntry*>(const_cast<void*>(a.log_table)),
+                                                        (double)a.stop_distance, (double)a.free_distance);
     if (n_faces > 0) prepare_faces_kernel<R><<<(n_faces + 255) / 256, 256, 0, stream>>>(n_faces, a.face_vec, face_unit);
     const int L = a.lights_per_replica > 0 && a.n_lights > 0 ? a.n_lights / a.n_replicas : 0;
     if (L > 0) fill_i32_kernel<<<(2 * L + 255) / 256, 256, 0, stream>>>(reinterpret_cast<int32_t*>(a.light_cellinfo), (size_t)2 * L, -1);
