@@ -210,6 +210,7 @@ void fill_args(const tb2_sim* s, StepArgsT<R>* a) {
     a->agent_car = c.agent_car; a->step_index = (int32_t)s->steps;
     a->speed_limit = (R)c.speed_limit; a->stop_distance = (R)c.stop_distance; a->free_distance = (R)c.free_distance;
     a->default_acceleration = (R)c.default_acceleration;
+    a->inv_free_distance = (R)(1.0 / c.free_distance);
     a->log_table = s->buf<char>(B_LOG_TABLE);
     a->log_scale = (R)(128.0 / (c.free_distance - c.stop_distance));
     a->log_stop = (R)std::log(c.stop_distance);

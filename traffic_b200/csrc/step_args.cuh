@@ -62,6 +62,7 @@ struct StepArgsT {
     int32_t skip_insert;
     int32_t pipe_ctas;           // > 0: launch the software-pipelined persistent kernel with this many car CTAs   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
     R speed_limit, stop_distance, free_distance, default_acceleration;
+    R inv_free_distance;
     const void* log_table;   // LogEntry[TB2_LOG_N]: log over (stop, free] (see log_stop_free)
     R log_scale;             // TB2_LOG_N / (free - stop)
     R log_stop, inv_log_free_over_stop;  // host libm log(stop), 1/log(free/stop): simulation.obstacle_factor, simulation.py:180

@@ -74,9 +74,44 @@ __device__ __forceinline__ double rcp_(double v) { return __drcp_rn(v); }
 __device__ __forceinline__ float rcp_(float v) { return 1.0f / v; }
 __device__ __forceinline__ double log_(double v) { return log(v); }
 __device__ __forceinline__ float log_(float v) { return logf(v); }
+// sin(x + q*pi/2) for the arguments models.weigh_factors feeds it - distances over free_distance, a few radians, never
+// above 1e5: two-constant Cody-Waite reduction (exact product with the 33-bit head of pi/2) and the fdlibm kernel
+// polynomials, <= 1 ulp (2.2e-16 absolute) on [0, 100]; anything else takes libdevice.  ~20 instructions instead of ~45.
+__device__ __forceinline__ double sin_quadrant(double x, int q) {
+    if (!(fabs(x) < 1.0e5)) return q ? cos(x) : sin(x);
+    const double kf = rint(x * 0.6366197723675814);
+    double r = fma(-kf, 1.57079632673412561417e+00, x);
+    r = fma(-kf, 6.07710050650619224932e-11, r);
+    const int n = (int)kf + q;
+    const double z = r * r;
+    double v;
+    if (n & 1) {
+        double p = -1.13596475577881948265e-11;
+        p = fma(p, z, 2.08757232129817482790e-09);
+        p = fma(p, z, -2.75573143513906633035e-07);
+        p = fma(p, z, 2.48015872894767294178e-05);
+        p = fma(p, z, -1.38888888888741095749e-03);
+        p = fma(p, z, 4.16666666666666019037e-02);
+        v = fma(z * z, p, fma(-0.5, z, 1.0));
+    } else {
+        double p = 1.58969099521155010221e-10;
+        p = fma(p, z, -2.50507602534068634195e-08);
+        p = fma(p, z, 2.75573137070700676789e-06);
+        p = fma(p, z, -1.98412698298579493134e-04);
+        p = fma(p, z, 8.33333333332248946124e-03);
+        p = fma(p, z, -1.66666666666666324348e-01);
+        v = fma(p * z, r, r);
+    }
+    return (n & 2) ? -v : v;
+}
+#ifdef TB2_LIBDEVICE_TRIG
 __device__ __forceinline__ double cos_(double v) { return cos(v); }
-__device__ __forceinline__ float cos_(float v) { return cosf(v); }
 __device__ __forceinline__ double sin_(double v) { return sin(v); }
+#else
+__device__ __forceinline__ double cos_(double v) { return sin_quadrant(v, 1); }
+__device__ __forceinline__ double sin_(double v) { return sin_quadrant(v, 0); }
+#endif
+__device__ __forceinline__ float cos_(float v) { return cosf(v); }
 __device__ __forceinline__ float sin_(float v) { return sinf(v); }
 __device__ __forceinline__ double acos_(double v) { return acos(v); }
 __device__ __forceinline__ float acos_(float v) { return acosf(v); }
@@ -96,6 +131,17 @@ template <typename R>
 __device__ __forceinline__ R dot2(R ax, R ay, R bx, R by) { return fma(ay, by, ax * bx); }
 template <typename R>
 __device__ __forceinline__ R norm2(R x, R y) { return sqrt(dot2<R>(x, y, x, y)); }
+// distance-to-node and its reciprocal.  The distance itself must be the correctly rounded sqrt (np.linalg.norm): a leader
+// parked exactly on my target node makes `d_car > d_node` (simulation.py:120) an exact tie, which a 1-ulp shortcut
+// (d = dd * rsqrt(dd)) would break.
+__device__ __forceinline__ void norm2_inv(double x, double y, double& d, double& inv) {
+    d = sqrt(dot2<double>(x, y, x, y));
+    inv = __drcp_rn(d);
+}
+__device__ __forceinline__ void norm2_inv(float x, float y, float& d, float& inv) {
+    d = sqrtf(dot2<float>(x, y, x, y));
+    inv = 1.0f / d;
+}
 template <typename R>
 __device__ __forceinline__ R clip1(R c) { return c < R(-1) ? R(-1) : (c > R(1) ? R(1) : c); }
 
@@ -412,9 +458,28 @@ struct Rot {
 // AUX: also write the observation-only columns.  ENS: replica ensemble (per-replica cell records / face states, agent
 // arrival bookkeeping); a single simulation compiles these out.
 // ---------------------------------------------------------------------------------------------------------------
+// Operand providers of the segments: plain registers (one-launch-per-step and persistent small-world kernels) ...
+template <typename R>
+struct OwnRegs {
+    using R2 = typename real2<R>::type;
+    const StepArgsT<R>* a;
+    R2 t, hc_;
+    R rt_;
+    int cur, end, eff, c, sec_;
+    __device__ __forceinline__ R2 target() const { return t; }
+    __device__ __forceinline__ int3 route() const { return make_int3(cur, end, eff); }
+    __device__ __forceinline__ R2 hc() const { return hc_; }
+    __device__ __forceinline__ R rt() const { return rt_; }
+    __device__ __forceinline__ int cell() const { return c; }
+    __device__ __forceinline__ int sec() const { return sec_; }
+    __device__ __forceinline__ R2 next_curv() const { return a->pt_curv[cur + 1]; }
+    __device__ __forceinline__ CellStatT<R> stat() const { return a->cell_stat[c]; }
+};
+
 template <typename R>
 struct View {
     R x, y, dx, dy, d_node;   // (the target itself is re-fetched by the rare paths that need it: fewer live registers)
+    R inv_d;                  // 1 / d_node
     int nx, ny;          // int(|dx|), int(|dy|): lengths of the two linspaces
     bool has_path, crossed, spaces;
     int path_len;
@@ -444,7 +509,7 @@ __device__ __forceinline__ View<R> view_build(const StepArgsT<R>& a, typename re
     v.path_len = v.has_path ? end - cur : 0;
     v.crossed = crossed;
     v.dx = t.x - v.x; v.dy = t.y - v.y;
-    v.d_node = norm2<R>(v.dx, v.dy);
+    norm2_inv(v.dx, v.dy, v.d_node, v.inv_d);
     const Axis<R> ax = make_axis<R>(v.x, t.x), ay = make_axis<R>(v.y, t.y);
     v.nx = ax.n; v.ny = ay.n;
     v.spaces = axis_any<R>(ax, a.origin_x) && axis_any<R>(ay, a.origin_y);
@@ -469,11 +534,12 @@ __device__ __forceinline__ Axis<R> axis_of(R start, R stop, R delta, int n) {
 
 // navigation.car_obstacles (navigation.py:422-456) against candidate j at position o, then navigation.light_obstacles
 // (navigation.py:459-498) for a bin whose go word is gw; load_stat() yields the bin's static light record.
-// target(): the car's target point (only the exact / general fall-backs ask for it)
-template <typename R, typename LoadStat, typename Target>
+// own: provider of the car's staged operands (OwnRegs / OwnSmem); target() - the car's target point - is only asked for
+// by the exact / general fall-backs, stat() - the bin's static light record - only when the bin has a light.
+template <typename R, typename Own>
 __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fbase, int c,
                                            const View<R>& v, int j, typename real2<R>::type o, uint32_t gw,
-                                           LoadStat load_stat, Target target, R& d_car, int& lead, R& d_light) {
+                                           const Own& own, R& d_car, int& lead, R& d_light) {
     const Axis<R> ax = axis_of<R>(v.x, R(0), v.dx, v.nx), ay = axis_of<R>(v.y, R(0), v.dy, v.ny);
     const int nl = (int)(gw >> 16), nf0 = (int)((gw >> 8) & 0xffu);
     d_car = R(0);
@@ -484,11 +550,11 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
     [[maybe_unused]] AxisFilter ffx, ffy;
     if constexpr (is_f64<R>) { ffx = axis_filter(ax); ffy = axis_filter(ay); }
     auto on_x = [&](int kmin, R val) {
-        if constexpr (is_f64<R>) return on_axis(ax, ffx, kmin, val, [&]() { return target().x; });
+        if constexpr (is_f64<R>) return on_axis(ax, ffx, kmin, val, [&]() { return own.target().x; });
         else return on_axis(ax, kmin, val, a.origin_x);
     };
     auto on_y = [&](int kmin, R val) {
-        if constexpr (is_f64<R>) return on_axis(ay, ffy, kmin, val, [&]() { return target().y; });
+        if constexpr (is_f64<R>) return on_axis(ay, ffy, kmin, val, [&]() { return own.target().y; });
         else return on_axis(ay, kmin, val, a.origin_y);
     };
     if (j != TB2_EMPTY) {
@@ -499,10 +565,10 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
     }
     if (nl) {
         if (nf0 > 4) {
-            const typename real2<R>::type t = target();
+            const typename real2<R>::type t = own.target();
             d_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
         } else {
-            const CellStatT<R> st = load_stat();
+            const CellStatT<R> st = own.stat();
             if (on_x(1, st.xy0.x) && on_y(1, st.xy0.y)) {
                 // first light of the bin: faces from the static record (snorm16 units), go bits from the go word
                 const R cvx = st.xy0.x - v.x, cvy = st.xy0.y - v.y;
@@ -523,7 +589,7 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
                 if (!found && band) found = first_light_band_exact<R>(a, c, band, cvx, cvy);
                 if (found) d_light = norm2<R>(cvx, cvy);
                 else if (nl > 1) {
-                    const typename real2<R>::type t = target();
+                    const typename real2<R>::type t = own.target();
                     d_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, t.x, v.y, t.y);
                 }
                 else d_light = -R(0);   // lights exhausted -> None
@@ -556,20 +622,21 @@ __device__ __forceinline__ float log_stop_free(const LogEntry*, float d, float, 
 
 // next_curv(): curvature constants of the route point after the head (pt_curv[cur + 1]); insert(t, i, sec): table
 // insertion policy (immediate, or deferred by the pipelined kernel).
-// route(): (cursor, path_end, path_eff_end) of the car and target(): its target point - only the crossing / parking
-// branches ask for them.
-template <typename R, bool AUX, bool ENS, typename Route, typename Target, typename NextCurv, typename Insert>
+// own: provider of the car's staged operands, each fetched where it is used (route() = (cursor, path_end, path_eff_end),
+// target(), next_curv() only by the crossing / parking branches); insert(t, i, sec): table insertion policy (immediate,
+// or deferred by the pipelined kernel).
+template <typename R, bool AUX, bool ENS, typename Own, typename Insert>
 __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& rot, const LogEntry* __restrict__ logtab, int i,
-                                         int rep, const View<R>& v, R d_car, int lead, R d_light,
-                                         typename real2<R>::type hc, R rt, int c, int sec_next, Route route, Target target,
-                                         NextCurv next_curv, Insert insert) {
+                                         int rep, const View<R>& v, R d_car, int lead, R d_light, const Own& own,
+                                         Insert insert) {
     using R2 = typename real2<R>::type;
     const int cbase = rep * a.g.n_cells, ibase = rep * a.cars_per_replica;
     const R x = v.x, y = v.y, d_node = v.d_node;
     // ---- velocity law + route advance (simulation.update_cars) ----
     R vx = R(0), vy = R(0);
     if (v.has_path) {
-        a.route_time[i] = rt + a.dt;
+        a.route_time[i] = own.rt() + a.dt;
+        const R2 hc = own.hc();
         // Both speed factors have the form log(d / den) / L on (stop, free]:
         //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den)
         //   simulation.obstacle_factor       (simulation.py:167-186): den = stop,            L = log(free/stop)
@@ -598,25 +665,25 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
             if (it == 0) r0 = r; else r1 = r;
         }
         R f = r0;   // curvature factor without an obstacle, obstacle factor with one
-        if (weigh) f = r0 * cos_(d_car / a.free_distance) + r1 * sin_(d_node / a.free_distance);  // models.py:41-66
+        // models.weigh_factors (models.py:41-66); d / free as d * (1/free): <= 1 ulp in the argument
+        if (weigh) f = r0 * cos_(d_car * a.inv_free_distance) + r1 * sin_(d_node * a.inv_free_distance);
         f = fabs(f);
         // unit(target - pos) * speed * factor (simulation.py:54-58) with one reciprocal instead of two divisions (<= 1 ulp)
-        const R inv_d = rcp_(d_node);
-        vx = v.dx * inv_d * a.speed_limit * f;
-        vy = v.dy * inv_d * a.speed_limit * f;
+        vx = v.dx * v.inv_d * a.speed_limit * f;
+        vy = v.dy * v.inv_d * a.speed_limit * f;
         if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) & isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
             const bool acc = !r_t && (!c_t || d_car > a.stop_distance);
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
         }
         if (v.crossed) {
-            const int3 q = route();   // (cur, end, eff)
+            const int3 q = own.route();   // (cur, end, eff)
             a.cursor[i] = q.x + 1;
             // new head: the point we just steered to, or the destination once no usable route point is left
-            a.head_xy[i] = (q.x + 1 >= q.z && v.path_len >= 2) ? a.dest_xy[i] : target();
-            if (q.x + 1 < q.y) a.head_curv[i] = next_curv();
+            a.head_xy[i] = (q.x + 1 >= q.z && v.path_len >= 2) ? a.dest_xy[i] : own.target();
+            if (q.x + 1 < q.y) a.head_curv[i] = own.next_curv();
         }
     } else {
-        const int3 q = route();
+        const int3 q = own.route();
         if (q.x != q.y) a.cursor[i] = q.y;  // path becomes []
     }
     const R xn = x + vx * a.dt, yn = y + vy * a.dt;  // cars.py:89-90
@@ -627,20 +694,21 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         a.d_car[i] = d_car;
         a.d_light[i] = d_light;
         a.leader[i] = lead >= 0 ? lead - ibase : -1;
-        a.cell_prev[i] = c;
+        a.cell_prev[i] = own.cell();
     }
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
+    const int c = own.cell();
     if (cn != c) a.cell[i] = cn;
     // (a car that changed bin has no prefetched entry of its new bin: it simply takes the atomics, ~1 % of the cars)
-    if (!a.skip_insert) insert(&a.cell_dyn[cbase + cn].w[2 * rot.tab_next_k], i, cn == c ? sec_next : TB2_EMPTY);
+    if (!a.skip_insert) insert(&a.cell_dyn[cbase + cn].w[2 * rot.tab_next_k], i, cn == c ? own.sec() : TB2_EMPTY);
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
         const R2 d = a.dest_xy[i];
         if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
             a.done[rep] = 1;
-            a.trip_time[rep] = (double)rt;
+            a.trip_time[rep] = (double)own.rt();
             a.trip_step[rep] = rot.step_index;
         }
     }
@@ -675,15 +743,13 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     R2 o = mk2(R(0), R(0));
     if (j != TB2_EMPTY) o = __ldcg(&rot.pos_in[j]);
 
-    R2 t;
-    const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff, t);
+    OwnRegs<R> own;
+    own.a = &a; own.cur = cur; own.end = end; own.eff = eff; own.c = c; own.sec_ = sec_next; own.hc_ = hc; own.rt_ = rt;
+    const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff, own.t);
     R d_car, d_light;
     int lead;
-    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, [&]() { return a.cell_stat[c]; }, [&]() { return t; }, d_car, lead,
-                  d_light);
-    seg_move<R, AUX, ENS>(a, rot, logtab, i, rep, v, d_car, lead, d_light, hc, rt, c, sec_next,
-                          [&]() { return make_int3(cur, end, eff); }, [&]() { return t; },
-                          [&]() { return a.pt_curv[cur + 1]; },
+    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, own, d_car, lead, d_light);
+    seg_move<R, AUX, ENS>(a, rot, logtab, i, rep, v, d_car, lead, d_light, own,
                           [](int32_t* t, int ii, int sec) { table_insert(t, ii, sec); });
 }
 
@@ -767,6 +833,27 @@ struct PipeSmemT {
     R2 ncurv[TB2_PIPE_BLOCK];      // crossing step: curvature constants of the next route point
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
+};
+
+// ... or the thread's staging slots in shared memory (pipelined kernel)
+template <typename R>
+struct OwnSmem {
+    using R2 = typename real2<R>::type;
+    const PipeSmemT<R>* sm;
+    int s, tid;
+    bool crossed;
+    __device__ __forceinline__ R2 target() const { return crossed ? sm->tgt[s][tid] : sm->head[s][tid]; }
+    __device__ __forceinline__ int3 route() const { return make_int3(sm->cur[s][tid], sm->end[s][tid], sm->eff[s][tid]); }
+    __device__ __forceinline__ R2 hc() const { return sm->hc[tid]; }
+    __device__ __forceinline__ R rt() const { return sm->rt[tid]; }
+    __device__ __forceinline__ int cell() const { return sm->cell[s][tid]; }
+    __device__ __forceinline__ int sec() const { return sm->sec[s][tid]; }
+    __device__ __forceinline__ R2 next_curv() const { return sm->ncurv[tid]; }
+    __device__ __forceinline__ CellStatT<R> stat() const {
+        union { CellStatT<R> st; int4 q[2]; } u;
+        u.q[0] = sm->st_lo[tid]; u.q[1] = sm->st_hi[tid];
+        return u.st;
+    }
 };
 
 template <typename R, bool AUX, bool ENS>
@@ -879,14 +966,12 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
         prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
         issue_late(i);                      // pending: G3(k), G1(k+1), GL(k)
         View<R> v{};
-        // the staged copies stay in shared memory; whoever needs one of them again re-reads it (LDS) instead of keeping
-        // it in a register across the fp64 sections
-        auto target = [&]() { return v.crossed ? sm.tgt[s][tid] : sm.head[s][tid]; };
-        auto route = [&]() { return make_int3(sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid]); };
+        // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
+        // instead of keeping it in a register across the fp64 sections
+        OwnSmem<R> own{&sm, s, tid, false};
         if (live) {
-            const bool crossed = sm.crossed[tid] != 0;
-            v = view_build<R>(a, sm.pos[s][tid], crossed ? sm.tgt[s][tid] : sm.head[s][tid], sm.cur[s][tid], sm.end[s][tid],
-                              sm.eff[s][tid], crossed);
+            own.crossed = sm.crossed[tid] != 0;
+            v = view_build<R>(a, sm.pos[s][tid], own.target(), sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid], own.crossed);
         }
         finish_insert(i - stride);
         cp_async_wait<2>();                 // G3(k) landed
@@ -896,20 +981,13 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
             const int2 m = sm.m[s][tid];
             const int j = (m.x != i) ? m.x : m.y;
             seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
-                          (uint32_t)sm.gw[s][tid],
-                          [&]() {
-                              union { CellStatT<R> st; int4 q[2]; } u;
-                              u.q[0] = sm.st_lo[tid]; u.q[1] = sm.st_hi[tid];
-                              return u.st;
-                          },
-                          target, d_car, lead, d_light);
+                          (uint32_t)sm.gw[s][tid], own, d_car, lead, d_light);
         }
         cp_async_wait<1>();                 // G1(k+1) landed
         issue_dyn(i + stride, s ^ 1);       // pending: GL(k), G2(k+1)
         cp_async_wait<1>();                 // GL(k) landed
         if (live)
-            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, sm.hc[tid], sm.rt[tid],
-                                  sm.cell[s][tid], sm.sec[s][tid], route, target, [&]() { return sm.ncurv[tid]; },
+            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, own,
                                   [&](int32_t* t, int ii, int sec) {
                                       if (ii > sec) return;
                                       pend_old = atomicMin(t, ii);
