@@ -472,8 +472,17 @@ struct OwnRegs {
     __device__ __forceinline__ R rt() const { return rt_; }
     __device__ __forceinline__ int cell() const { return c; }
     __device__ __forceinline__ int sec() const { return sec_; }
-    __device__ __forceinline__ R2 next_curv() const { return a->pt_curv[cur + 1]; }
+    __device__ __forceinline__ R2 next_curv(int q) const { return a->pt_curv[q]; }
     __device__ __forceinline__ CellStatT<R> stat() const { return a->cell_stat[c]; }
+    // results go straight to the global columns
+    R2* pos_out;
+    __device__ __forceinline__ void store_route_time(int i, R v) { a->route_time[i] = v; }
+    __device__ __forceinline__ void store_cursor(int i, int v) { a->cursor[i] = v; }
+    __device__ __forceinline__ void store_head(int i, R2 v) { a->head_xy[i] = v; }
+    __device__ __forceinline__ void store_head_curv(int i, R2 v) { a->head_curv[i] = v; }
+    __device__ __forceinline__ void store_pos(int i, R2 v) { pos_out[i] = v; }
+    __device__ __forceinline__ void store_cell(int i, int v) { a->cell[i] = v; }
+    __device__ __forceinline__ void on_done() {}
 };
 
 template <typename R>
@@ -627,15 +636,16 @@ __device__ __forceinline__ float log_stop_free(const LogEntry*, float d, float, 
 // or deferred by the pipelined kernel).
 template <typename R, bool AUX, bool ENS, typename Own, typename Insert>
 __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& rot, const LogEntry* __restrict__ logtab, int i,
-                                         int rep, const View<R>& v, R d_car, int lead, R d_light, const Own& own,
+                                         int rep, const View<R>& v, R d_car, int lead, R d_light, Own& own,
                                          Insert insert) {
     using R2 = typename real2<R>::type;
     const int cbase = rep * a.g.n_cells, ibase = rep * a.cars_per_replica;
     const R x = v.x, y = v.y, d_node = v.d_node;
+    [[maybe_unused]] const R rt0 = ENS ? own.rt() : R(0);   // start-of-step route time (arrival bookkeeping)
     // ---- velocity law + route advance (simulation.update_cars) ----
     R vx = R(0), vy = R(0);
     if (v.has_path) {
-        a.route_time[i] = own.rt() + a.dt;
+        own.store_route_time(i, own.rt() + a.dt);
         const R2 hc = own.hc();
         // Both speed factors have the form log(d / den) / L on (stop, free]:
         //   simulation.road_curvature_factor (simulation.py:135-164): den = stop*2*theta/pi, L = log(free/den)
@@ -677,39 +687,42 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         }
         if (v.crossed) {
             const int3 q = own.route();   // (cur, end, eff)
-            a.cursor[i] = q.x + 1;
             // new head: the point we just steered to, or the destination once no usable route point is left
-            a.head_xy[i] = (q.x + 1 >= q.z && v.path_len >= 2) ? a.dest_xy[i] : own.target();
-            if (q.x + 1 < q.y) a.head_curv[i] = own.next_curv();
+            const R2 nh = (q.x + 1 >= q.z && v.path_len >= 2) ? a.dest_xy[i] : own.target();
+            own.store_cursor(i, q.x + 1);
+            own.store_head(i, nh);
+            if (q.x + 1 < q.y) own.store_head_curv(i, own.next_curv(q.x + 1));
         }
     } else {
         const int3 q = own.route();
-        if (q.x != q.y) a.cursor[i] = q.y;  // path becomes []
+        if (q.x != q.y) own.store_cursor(i, q.y);  // path becomes []
     }
     const R xn = x + vx * a.dt, yn = y + vy * a.dt;  // cars.py:89-90
-    rot.pos_out[i] = mk2(xn, yn);
+    const int c = own.cell();
+    own.store_pos(i, mk2(xn, yn));
     if (AUX) {
         a.vel[i] = mk2(vx, vy);
         a.d_node[i] = d_node;
         a.d_car[i] = d_car;
         a.d_light[i] = d_light;
         a.leader[i] = lead >= 0 ? lead - ibase : -1;
-        a.cell_prev[i] = own.cell();
+        a.cell_prev[i] = c;
     }
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
-    const int c = own.cell();
-    if (cn != c) a.cell[i] = cn;
+    const int sec = own.sec();
+    if (cn != c) own.store_cell(i, cn);
     // (a car that changed bin has no prefetched entry of its new bin: it simply takes the atomics, ~1 % of the cars)
-    if (!a.skip_insert) insert(&a.cell_dyn[cbase + cn].w[2 * rot.tab_next_k], i, cn == c ? own.sec() : TB2_EMPTY);
+    if (!a.skip_insert) insert(cbase + cn, i, cn == c ? sec : TB2_EMPTY);
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
         const R2 d = a.dest_xy[i];
         if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
             a.done[rep] = 1;
-            a.trip_time[rep] = (double)own.rt();
+            a.trip_time[rep] = (double)rt0;
             a.trip_step[rep] = rot.step_index;
+            own.on_done();
         }
     }
 }
@@ -744,13 +757,13 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     if (j != TB2_EMPTY) o = __ldcg(&rot.pos_in[j]);
 
     OwnRegs<R> own;
-    own.a = &a; own.cur = cur; own.end = end; own.eff = eff; own.c = c; own.sec_ = sec_next; own.hc_ = hc; own.rt_ = rt;
+    own.a = &a; own.pos_out = rot.pos_out; own.cur = cur; own.end = end; own.eff = eff; own.c = c; own.sec_ = sec_next; own.hc_ = hc; own.rt_ = rt;
     const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff, own.t);
     R d_car, d_light;
     int lead;
     seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, own, d_car, lead, d_light);
     seg_move<R, AUX, ENS>(a, rot, logtab, i, rep, v, d_car, lead, d_light, own,
-                          [](int32_t* t, int ii, int sec) { table_insert(t, ii, sec); });
+                          [&](int rec, int ii, int sec) { table_insert(&a.cell_dyn[rec].w[2 * rot.tab_next_k], ii, sec); });
 }
 
 // every CTA keeps the (stop, free] log table in shared memory; the caller synchronises the CTA afterwards
@@ -842,13 +855,22 @@ struct OwnSmem {
     const PipeSmemT<R>* sm;
     int s, tid;
     bool crossed;
+    const StepArgsT<R>* a;
+    R2* pos_out;
+    __device__ __forceinline__ void store_route_time(int i, R v) { a->route_time[i] = v; }
+    __device__ __forceinline__ void store_cursor(int i, int v) { a->cursor[i] = v; }
+    __device__ __forceinline__ void store_head(int i, R2 v) { a->head_xy[i] = v; }
+    __device__ __forceinline__ void store_head_curv(int i, R2 v) { a->head_curv[i] = v; }
+    __device__ __forceinline__ void store_pos(int i, R2 v) { pos_out[i] = v; }
+    __device__ __forceinline__ void store_cell(int i, int v) { a->cell[i] = v; }
+    __device__ __forceinline__ void on_done() {}
     __device__ __forceinline__ R2 target() const { return crossed ? sm->tgt[s][tid] : sm->head[s][tid]; }
     __device__ __forceinline__ int3 route() const { return make_int3(sm->cur[s][tid], sm->end[s][tid], sm->eff[s][tid]); }
     __device__ __forceinline__ R2 hc() const { return sm->hc[tid]; }
     __device__ __forceinline__ R rt() const { return sm->rt[tid]; }
     __device__ __forceinline__ int cell() const { return sm->cell[s][tid]; }
     __device__ __forceinline__ int sec() const { return sm->sec[s][tid]; }
-    __device__ __forceinline__ R2 next_curv() const { return sm->ncurv[tid]; }
+    __device__ __forceinline__ R2 next_curv(int) const { return sm->ncurv[tid]; }
     __device__ __forceinline__ CellStatT<R> stat() const {
         union { CellStatT<R> st; int4 q[2]; } u;
         u.q[0] = sm->st_lo[tid]; u.q[1] = sm->st_hi[tid];
@@ -941,12 +963,16 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
     // from the youngest, so groups are committed in the order the loop consumes them: pending = [G3(0), G1(1)].
     // The first tile's operands are requested before anything else; the log table and the reset of the table that the
     // launch after next will fill ride in the shadow of that first HBM round trip. ----
+    {   // the log table travels with the first group (no synchronous load at the head of the kernel)
+        const char* src = reinterpret_cast<const char*>(a.log_table);
+        char* dst = reinterpret_cast<char*>(sm.logtab);
+        for (int k = tid * 16; k < (int)sizeof(sm.logtab); k += B * 16) cp_async<16>(dst + k, src + k);
+    }
     issue_early(i, 0);
     for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
-    load_log_table(sm.logtab, reinterpret_cast<const LogEntry*>(a.log_table));
     clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
-    __syncthreads();
     cp_async_wait<0>();
+    __syncthreads();   // every thread's slice of the log table has landed
     issue_dyn(i, 0);
     cp_async_wait<0>();
     issue_cand(i, 0);
@@ -968,7 +994,7 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
         View<R> v{};
         // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
         // instead of keeping it in a register across the fp64 sections
-        OwnSmem<R> own{&sm, s, tid, false};
+        OwnSmem<R> own{&sm, s, tid, false, &a, rot.pos_out};
         if (live) {
             own.crossed = sm.crossed[tid] != 0;
             v = view_build<R>(a, sm.pos[s][tid], own.target(), sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid], own.crossed);
@@ -988,10 +1014,10 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
         cp_async_wait<1>();                 // GL(k) landed
         if (live)
             seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, own,
-                                  [&](int32_t* t, int ii, int sec) {
+                                  [&](int rec, int ii, int sec) {
                                       if (ii > sec) return;
-                                      pend_old = atomicMin(t, ii);
-                                      pend_rec = (int)((reinterpret_cast<CellDynT*>(t - 2 * a.tab_next_k)) - a.cell_dyn);
+                                      pend_old = atomicMin(&a.cell_dyn[rec].w[2 * a.tab_next_k], ii);
+                                      pend_rec = rec;
                                   });
         cp_async_wait<0>();                 // G2(k+1) landed
         issue_cand(i + stride, s ^ 1);
