@@ -140,6 +140,14 @@ int tb2_lights_update(tb2_sim* sim, double dt, void* stream);
  * 123-133).  Asynchronous on `stream`. */
 int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stream);
 
+/* Replica ensembles (tb2_config.n_replicas, agent_car): the rollout loop of environment.Env.step / simulation_step
+ * (environment.py:97-173) - every replica advances until its agent satisfies FrontView.end_of_route
+ * (navigation.py:113-128, tested before each step) or max_steps is reached (the reference loop has no cap and may never
+ * terminate).  One launch: each replica is one thread-block cluster whose world stays on chip; a
+ * replica that has arrived leaves the launch and stays frozen in later calls.  Results: TB2_DONE / TB2_TRIP_TIME /
+ * TB2_TRIP_STEP.  TB2_ERR_STATE when the world does not fit the on-chip form (<= 4096 cars and lights per replica). */
+int tb2_rollout(tb2_sim* sim, double dt, int32_t max_steps, int32_t order, void* stream);
+
 /* End-to-end variant with HOST buffers (what Cars.update does for a caller that passes the lights DataFrame and
  * reads positions back, animate.py:63-69): optional H2D of the face states, n_steps, D2H of positions (frame_xy,
  * [N][2] in the sim's precision) and, when non-NULL, the face states.  Synchronises `stream` before returning. */

@@ -127,3 +127,50 @@ def test_ensemble_matches_one_oracle_run_per_replica(R, chunk):
             assert res[r, 2] == 1 and res[r, 1] == trip[1] and abs(res[r, 0] - trip[0]) < 1e-12
     assert res[:, 2].sum() >= 1, "test world: no agent arrived, pick a shorter route"
     assert len({tuple(ens.switch_time[r]) for r in range(R)}) == R
+
+
+@pytest.mark.gpu
+def test_rollout_launch_stops_each_replica_at_arrival():
+    """tb2_rollout: one launch, every replica (one thread-block cluster, world on chip) leaves when its agent has arrived;
+    trip time / steps / done must equal what the fixed-length batched run records, and an arrived replica stays frozen."""
+    from traffic_b200 import native, synth
+
+    w0, _ = synth.make_city(nx_=32, ny_=32, n_cars=1500, prescale=3, seed=21, max_hops=6)
+    dt, steps, R = 1e-3, 400, 6
+    lens = w0.path_end - w0.path_start
+    agent = int(np.flatnonzero((lens >= 1) & (lens <= 2))[0])
+    ref = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
+    ref.sim.step(dt, steps, native.ORDER_LIGHTS_CARS)
+    want = ref.results(steps)
+    ens = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
+    l0 = ens.sim.launch_count
+    got = ens.rollout(dt, steps)
+    assert ens.sim.launch_count - l0 == 1, "rollout must be a single launch"
+    assert np.array_equal(got[:, 1:], want[:, 1:]) and np.allclose(got[:, 0], want[:, 0], rtol=0, atol=1e-12)
+    again = ens.rollout(dt, 50)        # arrived replicas are frozen, the others keep going
+    arrived = got[:, 2] == 1
+    assert np.array_equal(again[arrived], got[arrived])
+    for r in np.flatnonzero(arrived):
+        # frozen at the arrival step: the agent's route time is the recorded trip time
+        rt = ens.sim.download(native.ROUTE_TIME).reshape(R, -1)[r, agent]
+        assert abs(rt - got[r, 0]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_rollout_batched_form_equals_cluster_resident_form(monkeypatch):
+    """Large ensembles take the batched HBM kernels (arrived replicas frozen, done flags read back every 256 steps);
+    forced here on a small ensemble, it must report exactly what the one-launch cluster-resident rollout reports."""
+    from traffic_b200 import native, synth
+
+    w0, _ = synth.make_city(nx_=32, ny_=32, n_cars=1500, prescale=3, seed=21, max_hops=6)
+    dt, steps, R = 1e-3, 600, 5
+    lens = w0.path_end - w0.path_start
+    agent = int(np.flatnonzero((lens >= 1) & (lens <= 2))[0])
+    outs = []
+    for no_res in ("0", "1"):
+        monkeypatch.setenv("TB2_NO_RESIDENT", no_res)
+        ens = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
+        outs.append(ens.rollout(dt, steps))
+    a, b = outs
+    assert a[:, 2].sum() >= 1
+    assert np.array_equal(a[:, 1:], b[:, 1:]) and np.allclose(a[:, 0], b[:, 0], rtol=0, atol=1e-12)

@@ -135,10 +135,12 @@ struct tb2_sim {
     int n_cells = 0;
     int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
+    bool freeze_done = false;       // inside tb2_rollout: arrived replicas are frozen
     bool go_dirty = false;          // TB2_FACE_GO was uploaded: the per-bin go words must be re-derived before the next step
     bool allow_pipe = true;         // TB2_NO_PIPE=1: big worlds use the plain one-thread-per-car kernel (A/B testing)
     bool force_pipe = false;        // TB2_FORCE_PIPE=1: every world goes through the pipelined kernel (test coverage)
     int n_sms = 0;
+    bool allow_resident = true;     // TB2_NO_RESIDENT=1: small worlds / ensembles use the global-memory kernels (A/B testing)
     bool allow_persistent = true;   // TB2_NO_PERSISTENT=1 in the environment forces one launch per step (A/B testing)
     int64_t launches = 0, steps = 0;
     double log_free_over_stop = 0.0;
@@ -294,6 +296,7 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
         else if (s->force_pipe && tiles > 0) a.pipe_ctas = tiles < resident ? tiles : resident;
     }
     a.skip_insert = s->cfg.neighbor_mode == TB2_NEIGHBOR_SORT;
+    a.freeze_done = s->freeze_done ? 1 : 0;
     launch_step(a, stream);
     if (a.skip_insert)   // north_star's pipeline: radix sort by bin + segment heads -> the same table
         s->launches += neighbor_sort_build(a.n_cars, a.cars_per_replica, s->n_cells, key_bits_of(s->cfg), a.cell,
@@ -302,9 +305,20 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
                                            s->buf<char>(B_SORT_TEMP), s->lay.bytes[B_SORT_TEMP], a.cell_dyn, a.tab_next_k, stream);
 }
 
+// The cluster-resident form is the low-latency form: it wins while every replica's cluster is co-resident (one CTA per
+// SM).  Larger ensembles are throughput problems and go through the batched HBM-streaming kernels (measured: 1,024
+// replicas x 2k cars run 2x faster batched - a step barrier per replica leaves the SMs idle).
+bool resident_ok(const tb2_sim* s) {
+    if (!(s->allow_resident && s->allow_persistent && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC && s->cfg.n_cars > 0))
+        return false;
+    const int cl = resident_fits(s->cfg.n_cars, s->cfg.n_lights, s->n_cells, s->cfg.precision == TB2_F32);
+    return cl > 0 && (int64_t)cl * s->cfg.n_replicas <= (s->n_sms > 0 ? s->n_sms : 1);
+}
+
 // All n_steps of a batch in one launch of the persistent cluster kernel (small worlds only).
 template <typename R>
-cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cudaStream_t stream) {
+cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cudaStream_t stream, bool resident = false,
+                              bool stop_when_done = false) {
     using R2 = typename real2<R>::type;
     StepArgsT<R> a{};
     fill_args<R>(s, &a);
@@ -317,7 +331,8 @@ cudaError_t step_persistent_t(tb2_sim* s, double dt, int n_steps, int order, cud
     pa.t[0] = s->buf<double>(B_T0); pa.t[1] = s->buf<double>(B_T1);
     pa.cur_pos = s->cur_pos; pa.cur_tab = s->cur_tab; pa.cur_go = s->cur_go; pa.cur_t = s->cur_t;
     pa.n_steps = n_steps; pa.order = order; pa.aux_last = s->cfg.write_aux;
-    return launch_persistent(a, pa, stream);
+    pa.stop_when_done = stop_when_done ? 1 : 0;
+    return resident ? launch_resident(a, pa, stream) : launch_persistent(a, pa, stream);
 }
 
 // Cars.update (cars.py:61-95), optionally with the lights tick fused into the trailing blocks of the same launch.
@@ -364,8 +379,9 @@ int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_s
     s->log_free_over_stop = std::log(cfg->free_distance / cfg->stop_distance);  // host libm, simulation.py:180
     if (const char* np = std::getenv("TB2_NO_PERSISTENT")) s->allow_persistent = !(np[0] == '1');
     if (const char* np = std::getenv("TB2_NO_PIPE")) s->allow_pipe = !(np[0] == '1');
+    if (const char* np = std::getenv("TB2_NO_RESIDENT")) s->allow_resident = !(np[0] == '1');
     if (const char* np = std::getenv("TB2_FORCE_PIPE")) s->force_pipe = (np[0] == '1');
-    if (s->force_pipe) s->allow_persistent = false;
+    if (s->force_pipe) { s->allow_persistent = false; s->allow_resident = false; }
     {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&s->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
@@ -491,6 +507,25 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
     if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
     if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_step before tb2_prepare (state was uploaded since)");
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_steps >= 2 && resident_ok(s)) {
+        // small world / replica ensemble: one cluster per replica, the world stays on chip for the whole batch
+        sync_go_words(s, stream);
+        const cudaError_t pe = s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, n_steps, order, stream, true)
+                                                           : step_persistent_t<float>(s, dt, n_steps, order, stream, true);
+        if (pe != cudaSuccess) {   // cluster launch refused (shared / partitioned device): never try again
+            (void)cudaGetLastError();
+            s->allow_resident = false;
+            return tb2_step(s, dt, n_steps, order, stream_);
+        }
+        s->launches++;
+        s->cur_pos ^= (n_steps & 1);
+        s->cur_tab = (s->cur_tab + n_steps) % 3;
+        s->cur_go ^= (n_steps & 1);      // n_steps ticks in either order
+        s->cur_t ^= (n_steps & 1);
+        s->steps += n_steps;
+        CU(cudaGetLastError());
+        return TB2_OK;
+    }
     if (s->allow_persistent && n_steps >= 2 && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC &&
         (int64_t)s->cfg.n_cars * s->cfg.n_replicas <= persistent_max_cars(s->cfg.precision == TB2_F32)) {
         // small world: the whole batch is one launch of the persistent cluster kernel
@@ -518,6 +553,53 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
         const int tick = (order == TB2_ORDER_CARS_LIGHTS) ? 1 : (k < n_steps - 1 ? 1 : 0);
         step_cars(s, dt, tick, (s->cfg.write_aux && k == n_steps - 1) ? 1 : 0, stream);
     }
+    CU(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_rollout(tb2_sim* s, double dt, int32_t max_steps, int32_t order, void* stream_) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    if (max_steps < 1) return fail(TB2_ERR_INVALID, "max_steps must be >= 1");
+    if (order != TB2_ORDER_CARS_LIGHTS && order != TB2_ORDER_LIGHTS_CARS) return fail(TB2_ERR_INVALID, "bad order");
+    if (s->cfg.agent_car < 0) return fail(TB2_ERR_INVALID, "tb2_rollout needs an agent car (tb2_config.agent_car)");
+    if (!s->prepared) return fail(TB2_ERR_STATE, "tb2_rollout before tb2_prepare (state was uploaded since)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!resident_ok(s)) {
+        // large ensembles: batched launches; the cars of an arrived replica stop moving, and every `chunk` steps the done
+        // flags (4 bytes per replica) are read back to leave as soon as every rollout is over
+        const int R = s->cfg.n_replicas, chunk = 256;
+        int32_t* done_h = nullptr;
+        CU(cudaMallocHost(reinterpret_cast<void**>(&done_h), sizeof(int32_t) * (size_t)R));
+        s->freeze_done = true;
+        int rc = TB2_OK;
+        const bool was_persistent = s->allow_persistent;
+        s->allow_persistent = false;   // per-step launches (the cooperative kernel has no frozen-replica path)
+        for (int32_t done_steps = 0; done_steps < max_steps && rc == TB2_OK;) {
+            const int32_t n = max_steps - done_steps < chunk ? max_steps - done_steps : chunk;
+            rc = tb2_step(s, dt, n, order, stream_);
+            done_steps += n;
+            if (rc != TB2_OK) break;
+            if (cudaMemcpyAsync(done_h, s->buf<int32_t>(B_DONE), sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaStreamSynchronize(stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "tb2_rollout readback"); break; }
+            bool all = true;
+            for (int r = 0; r < R && all; ++r) all = done_h[r] != 0;
+            if (all) break;
+        }
+        s->allow_persistent = was_persistent;
+        s->freeze_done = false;
+        cudaFreeHost(done_h);
+        return rc;
+    }
+    sync_go_words(s, stream);
+    const cudaError_t pe = s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, max_steps, order, stream, true, true)
+                                                       : step_persistent_t<float>(s, dt, max_steps, order, stream, true, true);
+    CU(pe);
+    s->launches++;
+    s->cur_pos ^= (max_steps & 1);
+    s->cur_tab = (s->cur_tab + max_steps) % 3;
+    s->cur_go ^= (max_steps & 1);
+    s->cur_t ^= (max_steps & 1);
+    s->steps += max_steps;
     CU(cudaGetLastError());
     return TB2_OK;
 }

@@ -60,6 +60,7 @@ struct StepArgsT {
     int32_t n_replicas, cars_per_replica, lights_per_replica, faces_per_replica;
     int32_t agent_car, step_index;
     int32_t skip_insert;
+    int32_t freeze_done;         // rollouts: cars of a replica whose agent has arrived no longer move (Env.step returned)
     int32_t pipe_ctas;           // > 0: launch the software-pipelined persistent kernel with this many car CTAs   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
     R speed_limit, stop_distance, free_distance, default_acceleration;
     R inv_free_distance;
@@ -122,7 +123,8 @@ struct PersistArgsT {
     uint8_t* go[2];
     double* t[2];
     int32_t cur_pos, cur_tab, cur_go, cur_t;
-    int32_t n_steps, order, aux_last, pad;
+    int32_t n_steps, order, aux_last;
+    int32_t stop_when_done;   // resident ensembles: a replica whose agent has arrived leaves the launch
 };
 
 using StepArgs64 = StepArgsT<double>;
@@ -137,6 +139,11 @@ int persistent_max_cars(int precision_f32);   // largest world the persistent (o
 int persistent_grid_capacity_f32();
 cudaError_t launch_persistent(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream);
 cudaError_t launch_persistent(const StepArgs32& a, const PersistArgsT<float>& pa, cudaStream_t stream);
+// one thread-block cluster per replica, world resident on chip (resident_kernel.cuh); cudaErrorInvalidConfiguration when
+// the world does not fit that form
+cudaError_t launch_resident(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream);
+cudaError_t launch_resident(const StepArgs32& a, const PersistArgsT<float>& pa, cudaStream_t stream);
+int resident_fits(int cars_per_replica, int lights_per_replica, int n_cells, int precision_f32);
 // (re)derive everything the step kernel keeps cached from the uploaded state: per-point curvature constants, per-car
 // head point + constants, unit face vectors, bins, and the cell table `cur_table` of the three in tab3 (all reset).
 void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, cudaStream_t stream);

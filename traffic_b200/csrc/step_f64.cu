@@ -1,6 +1,7 @@
 // fp64 ("parity mode") instantiation of the fused step kernel.  Compiled with --fmad=false: every multiply/add must
 // round separately, as numpy's ufuncs do (see step_kernel.cuh).
 #include "step_kernel.cuh"
+#include "resident_kernel.cuh"
 
 namespace {
 __global__ void __launch_bounds__(256) lights_tick_kernel(int n_lights, int lights_per_replica, int faces_per_replica,
@@ -51,4 +52,15 @@ void launch_lights_tick(int n_lights_total, int lights_per_replica, int faces_pe
     lights_tick_kernel<<<blocks, 256, 0, stream>>>(n_lights_total, lights_per_replica, faces_per_replica, n_cells, dt,
                                                    switch_time, face_ptr, go_cur, go_next, t_cur, t_next, light_cellinfo,
                                                    cell_dyn, go_k_next);
+}
+
+cudaError_t launch_resident(const StepArgs64& a, const PersistArgsT<double>& pa, cudaStream_t stream) {
+    return tb2k::launch_resident_t<double>(a, pa, stream);
+}
+int resident_fits(int cars_per_replica, int lights_per_replica, int n_cells, int precision_f32) {
+    const int cl = tb2k::resident_cluster_size(cars_per_replica);
+    if (cl == 0 || lights_per_replica > cl * TB2_RES_BLOCK) return 0;
+    const int slots = (n_cells + cl - 1) / cl;
+    const size_t smem = precision_f32 ? tb2k::ResidentLayout<float>::bytes(slots) : tb2k::ResidentLayout<double>::bytes(slots);
+    return smem <= 200 * 1024 ? cl : 0;   // the cluster size, 0 = does not fit
 }

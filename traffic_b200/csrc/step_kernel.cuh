@@ -737,6 +737,7 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     // replica of this car (1 for a single simulation): offsets into the per-replica cell records and face states
     const int rep = ENS ? i / a.cars_per_replica : 0;
     const int cbase = rep * a.g.n_cells, fbase = rep * a.faces_per_replica;
+    if (ENS && a.freeze_done && a.done[rep]) return;   // this rollout is over
     // ---- wave 1: own state ----
     const R2 p = rot.pos_in[i];
     const int cur = a.cursor[i];
@@ -987,8 +988,8 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
     };
     int s = 0;
     for (; i - tid < a.n_cars; i += stride, s ^= 1) {
-        const bool live = i < a.n_cars;
         const int rep = ENS ? i / a.cars_per_replica : 0;
+        const bool live = i < a.n_cars && !(ENS && a.freeze_done && a.done[rep]);   // (an arrived rollout is frozen)
         prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
         issue_late(i);                      // pending: G3(k), G1(k+1), GL(k)
         View<R> v{};

@@ -69,19 +69,14 @@ class Ensemble:
                                     agent_car=agent_car, switch_time=self.switch_time)
         self.agent_car = agent_car
 
-    def rollout(self, dt: float, max_steps: int, chunk: int = 500, order: int = native.ORDER_LIGHTS_CARS):
+    def rollout(self, dt: float, max_steps: int, order: int = native.ORDER_LIGHTS_CARS):
         """Advance until every replica's agent has arrived or ``max_steps`` (the reference loop has no cap and may
         spin forever).  Returns float64 ``[R, 4]``: trip_time, steps, done, replica id."""
-        steps = 0
-        done = None
-        while steps < max_steps:
-            n = min(chunk, max_steps - steps)
-            self.sim.step(dt, n, order)
-            steps += n
-            done = self.sim.tensor(native.DONE)
-            if bool((done != 0).all().item()):   # one 4-byte-per-replica readback per chunk
-                break
-        return self.results(steps)
+        # tb2_rollout: small ensembles run as ONE launch (one thread-block cluster per replica, world on chip, a replica
+        # leaves when its agent has arrived); large ones as batched launches with arrived replicas frozen and a 4-byte
+        # per replica readback every 256 steps
+        self.sim.rollout(dt, max_steps, order)
+        return self.results(max_steps)
 
     def results(self, steps_run: int):
         done = self.sim.download(native.DONE)

@@ -34,7 +34,7 @@ FIELD_COUNT = 24
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
            "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
            "tb2_launch_count", "tb2_step_count", "tb2_route_paths", "tb2_route_last_error", "tb2_step_host_async",
-           "tb2_frame_wait"]
+           "tb2_frame_wait", "tb2_rollout"]
 
 
 class Tb2Config(C.Structure):
@@ -88,6 +88,7 @@ def lib():
         L.tb2_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.tb2_prepare.argtypes = [C.c_void_p, C.c_void_p]
         L.tb2_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
+        L.tb2_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
         L.tb2_step_host.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
         L.tb2_step_host_async.argtypes = L.tb2_step_host.argtypes
@@ -243,6 +244,12 @@ class DeviceSim:
     def step(self, dt: float, n_steps: int = 1, order: int = ORDER_CARS_LIGHTS):
         with self._torch.cuda.device(self.device):
             _check(self.L.tb2_step(self.h, C.c_double(dt), C.c_int32(n_steps), C.c_int32(order), self._stream()), "tb2_step")
+
+    def rollout(self, dt: float, max_steps: int, order: int = ORDER_LIGHTS_CARS):
+        """``Env.step``'s rollout loop for every replica in one launch (``tb2_rollout``)."""
+        with self._torch.cuda.device(self.device):
+            _check(self.L.tb2_rollout(self.h, C.c_double(dt), C.c_int32(max_steps), C.c_int32(order), self._stream()),
+                   "tb2_rollout")
 
     def cars_update(self, dt: float):
         with self._torch.cuda.device(self.device):
