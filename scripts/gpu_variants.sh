@@ -7,6 +7,6 @@ for kv in "$@"; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/variant_$name.json"))
-print("$name", "value %.4g"%d["value"], "us/step %.2f"%(d["ms_per_step"]*1e3), "frac %.3f"%d["roofline"]["frac"], "e2e %.4g"%d["e2e"]["value"], "2k us/step %.2f"%d["also"]["us_per_step"])
+print("$name", "value %.4g"%d["value"], "us/step %.2f"%(d["ms_per_step"]*1e3), "frac %.3f"%d["roofline"]["frac"], "e2e %.4g"%d["e2e"]["value"], "2k us/step %.2f"%d["small_world"]["us_per_step"])
 PY
 done

@@ -174,3 +174,18 @@ def test_rollout_batched_form_equals_cluster_resident_form(monkeypatch):
     a, b = outs
     assert a[:, 2].sum() >= 1
     assert np.array_equal(a[:, 1:], b[:, 1:]) and np.allclose(a[:, 0], b[:, 0], rtol=0, atol=1e-12)
+
+
+def test_reward_matches_the_reference_env_step_fixture():
+    """ensemble.reward / rewards_of against (reward, done) recorded from the unmodified reference's Env.step
+    (oracle/ref_env_rewards.py -> tests/golden/env_rewards.json)."""
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "env_rewards.json")))
+    assert len(fx["cases"]) >= 8
+    for case in fx["cases"]:
+        t, dt = case["trip_times"], case["dt"]
+        for k, (r_ref, done_ref) in enumerate(case["expected"]):
+            r, done = ensemble.reward(t[:k + 1], (k, len(t)), dt)
+            assert done == done_ref and abs(r - r_ref) <= 1e-12, (case["dt"], k, r, r_ref)
+        assert np.allclose(ensemble.rewards_of(t, dt), [e[0] for e in case["expected"]], rtol=0, atol=1e-12)
+    assert any(d for c in fx["cases"] for _, d in c["expected"]), "fixture never exercises the shortest-route bonus"

@@ -23,7 +23,7 @@
 #pragma once
 #include "step_kernel.cuh"
 
-#define TB2_RES_BLOCK 256
+#define TB2_RES_BLOCK 256        // largest CTA of the resident form (worlds up to 16 x 256 cars)
 #define TB2_RES_MAX_CTAS 16
 
 namespace tb2k {
@@ -63,18 +63,19 @@ template <typename R>
 struct ResidentLayout {
     using R2 = typename real2<R>::type;
     static __host__ __device__ size_t pos_off() { return 0; }
-    static __host__ __device__ size_t log_off() { return 2 * TB2_RES_BLOCK * sizeof(R2); }
+    static __host__ __device__ size_t log_off() { return 2 * TB2_RES_BLOCK * sizeof(R2); }   // (sized for the largest CTA)
     static __host__ __device__ size_t dyn_off() { return log_off() + TB2_LOG_N * sizeof(LogEntry); }
     static __host__ __device__ size_t stat_off(int slots) { return dyn_off() + (size_t)slots * sizeof(CellDynT); }
     static __host__ __device__ size_t flag_off(int slots) { return stat_off(slots) + (size_t)slots * sizeof(CellStatT<R>); }
     static __host__ __device__ size_t bytes(int slots) { return flag_off(slots) + 16; }
 };
 
-template <typename R, bool ENS>
-__global__ void __launch_bounds__(TB2_RES_BLOCK, 1)
+// B = threads per CTA: 128 for worlds up to 2,048 cars (16 CTAs, one warp per SM sub-partition: the step is a latency
+// chain, spreading it over more SMs shortens it - 5.4 vs 5.9 us per step on the 2k-car world), 256 beyond.
+template <typename R, bool ENS, int B>
+__global__ void __launch_bounds__(B, 1)
 resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ PersistArgsT<R> pa) {
     using R2 = typename real2<R>::type;
-    constexpr int B = TB2_RES_BLOCK;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     cg::cluster_group cl = cg::this_cluster();
     const int CL = (int)cl.num_blocks();
@@ -236,9 +237,11 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
     if (complete && rank == 0 && tid == 0) { *pa.t[0] = l_t; *pa.t[1] = l_t; }
 }
 
+inline int resident_block_threads(int cars_per_replica) { return cars_per_replica <= 128 * TB2_RES_MAX_CTAS ? 128 : 256; }
 // smallest cluster that holds `cars` cars, 0 if the world does not fit the resident form
 inline int resident_cluster_size(int cars_per_replica) {
-    const int ctas = (cars_per_replica + TB2_RES_BLOCK - 1) / TB2_RES_BLOCK;
+    const int blk = resident_block_threads(cars_per_replica);
+    const int ctas = (cars_per_replica + blk - 1) / blk;
     if (ctas > TB2_RES_MAX_CTAS) return 0;
     int cl = 1;
     while (cl < ctas) cl *= 2;
@@ -253,7 +256,10 @@ cudaError_t launch_resident_t(const StepArgsT<R>& a, const PersistArgsT<R>& pa, 
     const size_t smem = ResidentLayout<R>::bytes(slots);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     const bool ens = a.n_replicas > 1 || a.agent_car >= 0;
-    void (*kern)(const StepArgsT<R>, const PersistArgsT<R>) = ens ? resident_kernel<R, true> : resident_kernel<R, false>;
+    const int blk = resident_block_threads(a.cars_per_replica);
+    void (*kern)(const StepArgsT<R>, const PersistArgsT<R>) =
+        blk == 128 ? (ens ? resident_kernel<R, true, 128> : resident_kernel<R, false, 128>)
+                   : (ens ? resident_kernel<R, true, 256> : resident_kernel<R, false, 256>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (cl > 8) {
@@ -262,7 +268,7 @@ cudaError_t launch_resident_t(const StepArgsT<R>& a, const PersistArgsT<R>& pa, 
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cl * a.n_replicas, 1, 1);
-    cfg.blockDim = dim3(TB2_RES_BLOCK, 1, 1);
+    cfg.blockDim = dim3(blk, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

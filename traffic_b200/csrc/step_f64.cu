@@ -59,7 +59,7 @@ cudaError_t launch_resident(const StepArgs64& a, const PersistArgsT<double>& pa,
 }
 int resident_fits(int cars_per_replica, int lights_per_replica, int n_cells, int precision_f32) {
     const int cl = tb2k::resident_cluster_size(cars_per_replica);
-    if (cl == 0 || lights_per_replica > cl * TB2_RES_BLOCK) return 0;
+    if (cl == 0 || lights_per_replica > cl * tb2k::resident_block_threads(cars_per_replica)) return 0;
     const int slots = (n_cells + cl - 1) / cl;
     const size_t smem = precision_f32 ? tb2k::ResidentLayout<float>::bytes(slots) : tb2k::ResidentLayout<double>::bytes(slots);
     return smem <= 200 * 1024 ? cl : 0;   // the cluster size, 0 = does not fit

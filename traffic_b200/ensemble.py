@@ -33,6 +33,23 @@ def random_switch_times(world: World, n_replicas: int, seed: int):
     return out
 
 
+def pick_agent(world: World, min_points: int = 8, max_points: int = 24) -> int:
+    """A car whose rollout CAN terminate.  ``Env.simulation_step`` ends an episode when the agent is within 5 m of its
+    destination on BOTH axes (``navigation.py:113-128``), but a car parks as soon as it "crosses" its last route point - a
+    window of 1e-5 x |coordinate|, i.e. ~5.7 m in x but ~42 m in y at UTM scale - so only cars
+    whose last edge runs mostly along x get close enough.  ``learn.py``'s own choice (car 17) never arrives on most
+    worlds.  Returns the first car with a route of min_points..max_points points (long enough to meet lights, so that
+    the replicas' light timings matter) and an x-dominant last edge; falls back to any x-dominant route; -1 if none."""
+    lens = world.path_end - world.path_start
+    prev = np.where((lens >= 2)[:, None], world.path_xy[np.maximum(world.path_end - 2, 0)], world.pos)
+    last = world.path_xy[np.maximum(world.path_end - 1, 0)] - prev
+    xdom = (lens >= 2) & (np.abs(last[:, 0]) > 2.0 * np.abs(last[:, 1]))
+    idx = np.flatnonzero(xdom & (lens >= min_points) & (lens <= max_points))
+    if not len(idx):
+        idx = np.flatnonzero(xdom)
+    return int(idx[0]) if len(idx) else -1
+
+
 def reward(route_times, num, dt, high=10.0, thresh=5):
     """``Env.step`` reward for the episode whose trip time was just appended to ``route_times``
     (``environment.py:126-150``); ``num`` = (episode index, total)."""
@@ -49,6 +66,16 @@ def reward(route_times, num, dt, high=10.0, thresh=5):
         delta = route_times[num[0] - 1] - route_times[num[0]] + bonus
         r = delta if delta > 0 else 0.0
     return r, done
+
+
+def rewards_of(trip_times, dt, high=10.0, thresh=5):
+    """Rewards ``Env.step`` would hand out if the given trip times were successive episodes (``environment.py:126-150``):
+    episode k gets ``max(0, t[k-1] - t[k] + bonus)``, bonus = ``high`` when t[k] is within 5 dt of the best so far."""
+    out, seen = [], []
+    for k, t in enumerate(trip_times):
+        seen.append(t)
+        out.append(reward(seen, (k, len(trip_times)), dt, high, thresh)[0])
+    return np.asarray(out, np.float64)
 
 
 class Ensemble:
