@@ -125,6 +125,8 @@ void* tb2_field_ptr(const tb2_sim* sim, int field);
 /* src/dst: host or device memory; bytes must equal n_elems*elem_bytes */
 int tb2_upload(tb2_sim* sim, int field, const void* src, size_t bytes, void* stream);
 int tb2_download(const tb2_sim* sim, int field, void* dst, size_t bytes, void* stream);
+/* elements [first, first + count) of a field - what `state.loc[agent]` (environment.py:126,161) needs is one row */
+int tb2_download_range(const tb2_sim* sim, int field, size_t first, size_t count, void* dst, size_t bytes, void* stream);
 
 /* (re)build the cell -> two-smallest-car-index table from the current positions; call after uploading POS
  * (replaces the bin assignment at the end of the reference initialisers, simulation.py:246-250) */

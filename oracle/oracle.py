@@ -68,3 +68,25 @@ def run(w, dt: float, n_steps: int, order: int = ORDER_CARS_LIGHTS, threads: int
     # Cars.time_elapsed is a Python float running sum (cars.py:75)
     for _ in range(n_steps):
         w.cars_time += dt
+
+
+def cars_update(w, dt: float, threads: int | None = None) -> None:
+    """``Cars.update(dt, lights)`` alone (cars.py:61-95), lights untouched."""
+    L = lib()
+    L.to_set_threads(C.c_int(1 if threads is None else int(threads)))
+    P = params_of(w)
+    pos_new = np.empty((max(w.n_cars, 1), 2), np.float64)
+    min12 = np.empty(2 * w.grid.n_cells, np.int32)
+    L.to_cars_update(C.byref(P), C.c_double(dt), _p(w.pos), _p(w.vel), _p(w.route_time), _p(w.cursor), _p(w.path_end),
+                     _p(w.path_eff_end), _p(w.path_xy), _p(w.dest_xy), _p(w.d_node), _p(w.d_car), _p(w.d_light), _p(w.cell),
+                     _p(w.leader), _p(w.light_xy), _p(w.face_ptr), _p(w.face_vec), _p(w.face_go), _p(w.cell_light_ptr),
+                     _p(w.cell_light_idx), _p(pos_new), _p(min12))
+    w.cars_time += dt
+
+
+def lights_update(w, dt: float) -> None:
+    """``TrafficLights.update(dt)`` alone (cars.py:123-133)."""
+    L = lib()
+    t = C.c_double(w.lights_time)
+    L.to_lights_update(C.c_int(w.n_lights), C.byref(t), C.c_double(dt), _p(w.switch_time), _p(w.face_ptr), _p(w.face_go))
+    w.lights_time = t.value

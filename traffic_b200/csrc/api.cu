@@ -468,6 +468,17 @@ int tb2_download(const tb2_sim* s, int field, void* dst, size_t bytes, void* str
     return TB2_OK;
 }
 
+int tb2_download_range(const tb2_sim* s, int field, size_t first, size_t count, void* dst, size_t bytes, void* stream) {
+    if (!s) return fail(TB2_ERR_INVALID, "null sim");
+    int b; size_t eb, cnt;
+    if (int rc = field_buf(s, field, &b, &eb, &cnt)) return rc;
+    if (first > cnt || count > cnt - first) return fail(TB2_ERR_INVALID, "tb2_download_range: range outside the field");
+    if (bytes != eb * count) return fail(TB2_ERR_INVALID, "tb2_download_range: byte count does not match the range");
+    if (bytes && !dst) return fail(TB2_ERR_INVALID, "null destination");
+    if (bytes) CU(cudaMemcpyAsync(dst, s->arena + s->lay.off[b] + first * eb, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return TB2_OK;
+}
+
 int tb2_prepare(tb2_sim* s, void* stream_) {
     if (!s) return fail(TB2_ERR_INVALID, "null sim");
     cudaStream_t stream = (cudaStream_t)stream_;

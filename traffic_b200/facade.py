@@ -36,8 +36,27 @@ def _reference_params():
         return None
 
 
+class _LazyLoc:
+    """``state.loc``: a single integer row label is served from a few small device->host copies (what
+    ``Env.simulation_step`` / ``Env.step`` do every step, ``environment.py:126,161``); everything else falls through to
+    the fully materialised DataFrame."""
+
+    __slots__ = ("_owner",)
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def __getitem__(self, key):
+        row = getattr(self._owner, "_row", None)
+        if row is not None and isinstance(key, (int, np.integer)) and not isinstance(key, bool):
+            return row(int(key))
+        return self._owner._materialize().loc[key]
+
+
 class LazyFrame:
-    """Read-only stand-in for the reference's ``state`` DataFrame, materialised on first touch after each update."""
+    """Read-only stand-in for the reference's ``state`` DataFrame.  Device state is copied back only when it is looked
+    at, and only as much as is looked at: ``state[col]`` refreshes that column (group), ``state.loc[i]`` that row,
+    anything else (``iterrows``, arbitrary attribute access) the whole frame."""
 
     __slots__ = ("_owner",)
 
@@ -47,10 +66,17 @@ class LazyFrame:
     def _df(self):
         return self._owner._materialize()
 
+    @property
+    def loc(self):
+        return _LazyLoc(self._owner)
+
     def __getattr__(self, name):
         return getattr(self._df(), name)
 
     def __getitem__(self, key):
+        cols = getattr(self._owner, "_refresh_columns", None)
+        if cols is not None and (isinstance(key, str) or (isinstance(key, list) and all(isinstance(k, str) for k in key))):
+            return cols([key] if isinstance(key, str) else key)[key]
         return self._df()[key]
 
     def __setitem__(self, key, value):
@@ -92,8 +118,7 @@ class TrafficLights:
         # lights-only device simulation until a Cars object adopts these lights
         w = make_world(graph.axis, np.zeros((0, 2)), np.zeros(1, np.int64), np.zeros((0, 2)), np.zeros((0, 2)),
                        lights, cell)
-        self._sim = native.DeviceSim(w)
-        self._shared = False
+        self._sim = native.DeviceSim(w).retain()
 
     @property
     def state(self):
@@ -120,10 +145,27 @@ class TrafficLights:
     def _adopt(self, sim):
         """A Cars object built a combined simulation holding these lights: move onto it."""
         if self._sim is not sim:
-            if not self._shared:
-                self._sim.close()
-            self._sim = sim
-            self._shared = True
+            self._sim.release()
+            self._sim = sim.retain()
+
+
+# column groups of the cars DataFrame: one group = one (set of) device field(s)
+_GROUP_OF = {"x": "pos", "y": "pos", "vx": "vel", "vy": "vel", "route-time": "route-time",
+             "distance-to-node": "dist", "distance-to-car": "dist", "distance-to-red-light": "dist",
+             "xbin": "bins", "ybin": "bins", "xpath": "paths", "ypath": "paths", "route": "route"}
+_GROUPS = tuple(sorted(set(_GROUP_OF.values())))
+
+
+def _falsy(d, none):
+    """Mixed-type distance columns of the reference (Appendix B-4): a distance, False, or (lights only) None."""
+    out = d.astype(object)
+    zero = d == 0.0
+    if none:
+        out[zero & ~np.signbit(d)] = False
+        out[zero & np.signbit(d)] = None
+    else:
+        out[zero] = False
+    return out
 
 
 class Cars:
@@ -141,7 +183,7 @@ class Cars:
         self.stop_distance = 5
         self._frame = init_state.copy()
         self._n_rows = len(init_state)
-        self._dirty = False
+        self._stale = set()       # column groups of self._frame that are older than the device state
         self._state = LazyFrame(self)
         self._sim = None
         self._world = None
@@ -156,8 +198,9 @@ class Cars:
     # ------------------------------------------------------------------------------------------------------
     def _bind(self, lights):
         owner = lights._owner if isinstance(lights, LazyFrame) and isinstance(lights._owner, TrafficLights) else None
-        if self._sim is not None and owner is self._lights_owner and (owner is not None or lights is self._foreign):
-            return owner
+        if self._sim is not None and owner is self._lights_owner and (
+                (owner is not None and owner._sim is self._sim) or (owner is None and lights is self._foreign)):
+            return owner   # (owner._sim differs when another Cars object has adopted these lights since: rebind)
         lights_df = owner._materialize() if owner is not None else lights
         # current car state (if we are re-binding mid-run, continue from the device state)
         cars_df = self._materialize()
@@ -166,8 +209,8 @@ class Cars:
             w.lights_time = float(owner.time_elapsed)
         # (on a re-bind mid-run the frame's xpath/ypath already hold only the remaining route, so cursors carry over)
         if self._sim is not None:
-            self._sim.close()
-        self._sim = native.DeviceSim(w)
+            self._sim.release()    # a TrafficLights object that adopted it keeps it alive
+        self._sim = native.DeviceSim(w).retain()
         self._world = w
         self._path_start0 = w.path_start.copy()
         self._lights_owner = owner
@@ -185,7 +228,7 @@ class Cars:
             go = np.concatenate([np.asarray(v).astype(np.uint8) for v in lights["go-values"]]) if len(lights) else np.zeros(0, np.uint8)
             self._sim.upload(native.FACE_GO, go)
         self._sim.cars_update(dt)
-        self._dirty = True
+        self._stale = set(_GROUPS)
         self._updates += 1
         if self.serialize:
             self.write_state()
@@ -209,37 +252,86 @@ class Cars:
 
     # ------------------------------------------------------------------------------------------------------
     def _materialize(self):
-        if not self._dirty:
+        """The whole DataFrame, current (every stale column group is refreshed)."""
+        if self._stale:
+            self._refresh_columns(list(self._frame.columns))
+        return self._frame
+
+    def _refresh_columns(self, cols):
+        """Bring the column groups that hold ``cols`` up to date with the device; returns the frame."""
+        need = {_GROUP_OF[c] for c in cols if c in _GROUP_OF} & self._stale
+        if not need:
             return self._frame
-        w = self._sim.download_world(self._world)
-        f = self._frame
-        n = self._n_rows
-        f["x"], f["y"] = w.pos[:, 0], w.pos[:, 1]
-        f["vx"], f["vy"] = w.vel[:, 0], w.vel[:, 1]
-        f["route-time"] = w.route_time
-        f["distance-to-node"] = w.d_node
-        # mixed-type columns of the reference (Appendix B-4): a distance, False, or (lights only) None
-        dc = w.d_car.astype(object)
-        dc[w.d_car == 0.0] = False
-        dl = w.d_light.astype(object)
-        zero = w.d_light == 0.0
-        dl[zero & ~np.signbit(w.d_light)] = False
-        dl[zero & np.signbit(w.d_light)] = None
-        f["distance-to-car"] = dc
-        f["distance-to-red-light"] = dl
-        ncx = w.grid.ncx
-        f["xbin"] = (w.cell % ncx).astype(np.int64)
-        f["ybin"] = (w.cell // ncx).astype(np.int64)
-        # remaining route of every car as Python lists (the reference pops the head of these lists, simulation.py:47-52)
-        px, py = w.path_xy[:, 0].tolist(), w.path_xy[:, 1].tolist()
-        cur, end = w.cursor.tolist(), w.path_end.tolist()
-        xs = np.empty(n, object)
-        ys = np.empty(n, object)
-        for i, (a, b) in enumerate(zip(cur, end)):   # element-wise: numpy would broadcast equal-length lists to 2-D
-            xs[i] = px[a:b]
-            ys[i] = py[a:b]
-        f["xpath"], f["ypath"] = xs, ys
-        if self._updates > 0 and "route" in f.columns:
+        sim, f, w, n = self._sim, self._frame, self._world, self._n_rows
+        if "pos" in need:
+            pos = sim.download(native.POS).reshape(-1, 2).astype(np.float64)
+            if sim.precision != native.F64:
+                pos = pos + sim.origin
+            w.pos = pos
+            f["x"], f["y"] = pos[:, 0], pos[:, 1]
+        if "vel" in need:
+            w.vel = sim.download(native.VEL).reshape(-1, 2).astype(np.float64)
+            f["vx"], f["vy"] = w.vel[:, 0], w.vel[:, 1]
+        if "route-time" in need:
+            w.route_time = sim.download(native.ROUTE_TIME).astype(np.float64)
+            f["route-time"] = w.route_time
+        if "dist" in need:
+            w.d_node = sim.download(native.D_NODE).astype(np.float64)
+            w.d_car = sim.download(native.D_CAR).astype(np.float64)
+            w.d_light = sim.download(native.D_LIGHT).astype(np.float64)
+            f["distance-to-node"] = w.d_node
+            f["distance-to-car"] = _falsy(w.d_car, none=False)
+            f["distance-to-red-light"] = _falsy(w.d_light, none=True)
+        if "bins" in need:
+            w.cell = sim.download(native.CELL)
+            ncx = w.grid.ncx
+            f["xbin"] = (w.cell % ncx).astype(np.int64)
+            f["ybin"] = (w.cell // ncx).astype(np.int64)
+        if "paths" in need:
+            # remaining route of every car as Python lists (the reference pops the head of these lists, simulation.py:47-52)
+            w.cursor = sim.download(native.CURSOR)
+            px, py = w.path_xy[:, 0].tolist(), w.path_xy[:, 1].tolist()
+            cur, end = w.cursor.tolist(), w.path_end.tolist()
+            xs = np.empty(n, object)
+            ys = np.empty(n, object)
+            for i, (a, b) in enumerate(zip(cur, end)):   # element-wise: numpy would broadcast equal-length lists to 2-D
+                xs[i] = px[a:b]
+                ys[i] = py[a:b]
+            f["xpath"], f["ypath"] = xs, ys
+        if "route" in need and "route" in f.columns:
             f["route"] = np.nan  # the reference wipes this column on the first update (simulation.py:30,76; B-7)
-        self._dirty = False
+        self._stale -= need
         return f
+
+    def _row(self, i):
+        """``state.loc[i]`` as a Series: the stale cells of row i come from a few bytes of device memory each."""
+        f, sim, w = self._frame, self._sim, self._world
+        if not self._stale:
+            return f.loc[i]
+        if i < 0 or i >= self._n_rows:
+            raise KeyError(i)
+        row = f.loc[i].copy()
+        st = self._stale
+        if "pos" in st:
+            p = sim.download_range(native.POS, 2 * i, 2).astype(np.float64)
+            if sim.precision != native.F64:
+                p = p + sim.origin
+            row["x"], row["y"] = p[0], p[1]
+        if "vel" in st:
+            v = sim.download_range(native.VEL, 2 * i, 2)
+            row["vx"], row["vy"] = float(v[0]), float(v[1])
+        if "route-time" in st:
+            row["route-time"] = float(sim.download_range(native.ROUTE_TIME, i, 1)[0])
+        if "dist" in st:
+            row["distance-to-node"] = float(sim.download_range(native.D_NODE, i, 1)[0])
+            row["distance-to-car"] = _falsy(sim.download_range(native.D_CAR, i, 1).astype(np.float64), none=False)[0]
+            row["distance-to-red-light"] = _falsy(sim.download_range(native.D_LIGHT, i, 1).astype(np.float64), none=True)[0]
+        if "bins" in st:
+            c = int(sim.download_range(native.CELL, i, 1)[0])
+            row["xbin"], row["ybin"] = c % w.grid.ncx, c // w.grid.ncx
+        if "paths" in st:
+            a, b = int(sim.download_range(native.CURSOR, i, 1)[0]), int(w.path_end[i])
+            row["xpath"], row["ypath"] = w.path_xy[a:b, 0].tolist(), w.path_xy[a:b, 1].tolist()
+        if "route" in st and "route" in row.index:
+            row["route"] = np.nan
+        return row

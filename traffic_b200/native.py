@@ -34,7 +34,7 @@ FIELD_COUNT = 24
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
            "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
            "tb2_launch_count", "tb2_step_count", "tb2_route_paths", "tb2_route_last_error", "tb2_step_host_async",
-           "tb2_frame_wait", "tb2_rollout"]
+           "tb2_frame_wait", "tb2_rollout", "tb2_download_range"]
 
 
 class Tb2Config(C.Structure):
@@ -86,6 +86,7 @@ def lib():
         L.tb2_field_ptr.argtypes = [C.c_void_p, C.c_int]
         L.tb2_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.tb2_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.tb2_download_range.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         L.tb2_prepare.argtypes = [C.c_void_p, C.c_void_p]
         L.tb2_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
         L.tb2_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
@@ -164,6 +165,7 @@ class DeviceSim:
             _check(self.L.tb2_create(C.byref(self.cfg), C.c_void_p(self._arena_base), C.c_size_t(nbytes), C.byref(h)),
                    "tb2_create")
         self.h = h
+        self._refs = 0   # facade objects sharing this simulation (retain / release)
         self._keep = []  # host staging arrays that must outlive async copies
         self.upload_world(world)
 
@@ -177,8 +179,20 @@ class DeviceSim:
     def _dtype(self, field):
         return self._real() if field in _REAL_FIELDS else _NP_OF_FIELD[field]
 
+    def retain(self):
+        self._refs += 1
+        return self
+
+    def release(self):
+        """Drop one holder; the device simulation is destroyed when the last holder lets go."""
+        self._refs -= 1
+        if self._refs <= 0:
+            self.close()
+
     def upload(self, field: int, arr: np.ndarray):
         a = np.ascontiguousarray(arr, self._dtype(field))
+        if len(self._keep) >= 32:   # a driver loop that never reads state back must not pile up staging arrays
+            self.synchronize()
         self._keep.append(a)
         _check(self.L.tb2_upload(self.h, field, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes), self._stream()),
                "tb2_upload(%d)" % field)
@@ -190,6 +204,15 @@ class DeviceSim:
         assert out.itemsize == eb.value
         _check(self.L.tb2_download(self.h, field, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes), self._stream()),
                "tb2_download(%d)" % field)
+        self.synchronize()
+        return out
+
+    def download_range(self, field: int, first: int, count: int) -> np.ndarray:
+        """Elements [first, first + count) of a field (one small device->host copy)."""
+        out = np.empty(count, self._dtype(field))
+        _check(self.L.tb2_download_range(self.h, field, C.c_size_t(first), C.c_size_t(count),
+                                         out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes), self._stream()),
+               "tb2_download_range(%d)" % field)
         self.synchronize()
         return out
 
