@@ -77,3 +77,23 @@ def test_init_on_a_plain_networkx_graph_equals_array_path():
     for col in ("node", "degree", "x", "y", "switch-time", "xbin", "ybin"):
         assert np.array_equal(l1[col].to_numpy(), l2[col].to_numpy()), col
     assert all(a == b for a, b in zip(l1["out-xvectors"], l2["out-xvectors"]))
+
+
+def test_init_culdesac_reproduces_the_reference_fixture():
+    """init_culdesac_start_location (simulation.py:259-326) against the frame the unmodified reference built on the same
+    graph (oracle/ref_culdesac.py -> tests/golden/culdesac_init.json)."""
+    import json
+    import os
+    from traffic_b200 import init, synth
+
+    fx = json.load(open(os.path.join(util.GOLDEN_DIR, "culdesac_init.json")))
+    graph = synth.SynthGraph(**fx["graph"])
+    cars = init.init_culdesac_start_location(fx["n"], graph)
+    assert len(cars) == len(fx["cars"]) == fx["n"]
+    for (_, row), want in zip(cars.iterrows(), fx["cars"]):
+        assert row["origin"] == want["origin"] and row["destination"] == want["destination"]
+        assert list(row["route"]) == want["route"]
+        assert row["xpath"] == want["xpath"] and row["ypath"] == want["ypath"]
+        assert row["x"] == want["x"] and row["y"] == want["y"] and row["xbin"] == want["xbin"] and row["ybin"] == want["ybin"]
+    with pytest.raises(ValueError):
+        init.init_culdesac_start_location(fx["graph"]["culdesacs"] + 1, graph)

@@ -104,3 +104,55 @@ def test_polylines_with_edge_geometry():
     ptr2, xy2 = routing.polylines_with_geometry(node_xy, path_len, path_nodes, {})
     ptr3, xy3 = routing.polylines(node_xy, path_len, path_nodes)
     assert np.array_equal(ptr2, ptr3) and np.array_equal(xy2, xy3)
+
+
+@pytest.mark.gpu
+def test_zero_length_edges_and_self_loops_give_valid_routes():
+    """OSM twin / overlapping nodes produce zero-length edges (tight in both directions) and self-loops: the predecessor
+    walk must still terminate and return a shortest path (same length as networkx's, a valid edge sequence)."""
+    import networkx as nx
+    graph = synth.SynthGraph(12, 12, seed=2)
+    u, v, ln = list(graph.edge_u), list(graph.edge_v), list(graph.edge_len)
+    rng = np.random.default_rng(0)
+    n = graph.n_nodes
+    twins = rng.choice(n - 1, 25, replace=False)
+    for a in twins:                       # zero-length edges both ways + a zero-length self-loop + a 1e-13 m edge
+        u += [a, a + 1, a]; v += [a + 1, a, a]; ln += [0.0, 0.0, 0.0]
+    u += [3, 4]; v += [4, 3]; ln += [1e-13, 1e-13]
+    indptr, indices, w = routing.csr_of(n, u, v, ln)
+    origin = rng.integers(0, n, 300).astype(np.int32)
+    dest = rng.integers(0, n, 300).astype(np.int32)
+    path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origin, dest)
+    G = nx.MultiDiGraph()
+    G.add_nodes_from(range(n))
+    for a, b, c in zip(u, v, ln):
+        G.add_edge(int(a), int(b), length=float(c))
+    wmin = {}
+    for a, b, c in zip(u, v, ln):
+        wmin[(int(a), int(b))] = min(wmin.get((int(a), int(b)), np.inf), float(c))
+    for p in range(len(origin)):
+        want = nx.shortest_path_length(G, int(origin[p]), int(dest[p]), weight="length")
+        assert path_len[p] >= 1, "valid pair reported as no-path / overflow"
+        nodes = path_nodes[p, :path_len[p]].tolist()
+        assert nodes[0] == origin[p] and nodes[-1] == dest[p] and len(set(nodes)) == len(nodes)
+        got = sum(wmin[(a, b)] for a, b in zip(nodes[:-1], nodes[1:]))
+        assert abs(got - want) <= 1e-9 * max(1.0, want)
+
+
+@pytest.mark.gpu
+def test_routing_throughput_on_the_manhattan_grid():
+    """2,000 distinct origins on the 4,096-node grid (the reference: two networkx Dijkstras per car,
+    ~16 ms per car)."""
+    import time
+    graph = synth.SynthGraph(64, 64, seed=0)
+    indptr, indices, w = routing.csr_of(graph.n_nodes, graph.edge_u, graph.edge_v, graph.edge_len)
+    rng = np.random.default_rng(1)
+    origin = rng.choice(graph.n_nodes, 2000, replace=False).astype(np.int32)
+    dest = rng.integers(0, graph.n_nodes, 2000).astype(np.int32)
+    routing.shortest_paths(indptr, indices, w, origin[:8], dest[:8], max_len=256)      # warm up
+    t0 = time.perf_counter()
+    path_len, _ = routing.shortest_paths(indptr, indices, w, origin, dest, max_len=256)
+    el = time.perf_counter() - t0
+    assert (path_len >= 1).all()
+    print("routing: %d routes over %d distinct origins in %.1f ms = %.0f routes/s" % (len(origin), len(origin), el * 1e3, len(origin) / el))
+    assert len(origin) / el > 20000

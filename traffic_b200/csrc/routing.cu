@@ -21,35 +21,82 @@ namespace {
 
 constexpr unsigned long long kInfBits = 0x7ff0000000000000ull;  // +inf
 
+// One CTA per distinct origin.  SMEM = true: the distance labels, hop labels and the frontier flags of the whole graph
+// live in shared memory (graphs up to ~14k nodes) and are relaxed with shared-memory atomics; otherwise they live in
+// global memory.  Frontier driven: a sweep relaxes only the out-edges of nodes whose label changed in the previous sweep,
+// so the work is O(edges x a small factor) instead of O(nodes x sweeps).
+//
+// Predecessors are made acyclic by construction: after the distances have converged, hop labels are relaxed over the
+// TIGHT edges only (fl(dist[u] + w) == dist[v]) and pred[v] is the smallest u on a tight edge with hop[u] + 1 == hop[v].
+// A zero-length edge (OSM twin nodes) or a tiny length lost to rounding is tight in both directions, but hop labels
+// strictly decrease towards the origin, so the walk back always terminates (the predecessor graph is a tree).
+template <bool SMEM>
 __global__ void __launch_bounds__(256) sssp_kernel(int n_nodes, const int32_t* __restrict__ indptr,
                                                    const int32_t* __restrict__ indices, const double* __restrict__ weight,
                                                    const int32_t* __restrict__ sources, double limit,
-                                                   unsigned long long* dist_all, int32_t* pred_all) {
+                                                   unsigned long long* dist_all, int32_t* pred_all, int32_t* hop_all,
+                                                   uint8_t* flag_all) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int changed;
     const int s = blockIdx.x;
-    unsigned long long* dist = dist_all + (size_t)s * n_nodes;
+    unsigned long long* dist_g = dist_all + (size_t)s * n_nodes;
     int32_t* pred = pred_all + (size_t)s * n_nodes;
+    unsigned long long* dist = SMEM ? reinterpret_cast<unsigned long long*>(sm_raw) : dist_g;
+    int32_t* hop = SMEM ? reinterpret_cast<int32_t*>(sm_raw + (size_t)n_nodes * 8) : hop_all + (size_t)s * n_nodes;
+    uint8_t* flag0 = SMEM ? sm_raw + (size_t)n_nodes * 12 : flag_all + (size_t)s * 2 * n_nodes;
+    uint8_t* flag1 = flag0 + n_nodes;
     const int src = sources[s];
     for (int u = threadIdx.x; u < n_nodes; u += 256) {
         dist[u] = (u == src) ? 0ull : kInfBits;
+        hop[u] = (u == src) ? 0 : 0x7fffffff;
         pred[u] = 0x7fffffff;
+        flag0[u] = (u == src);
+        flag1[u] = 0;
     }
     __syncthreads();
-    for (int sweep = 0; sweep < n_nodes; ++sweep) {
+    // ---- distances: frontier-driven label correcting ----
+    uint8_t *cur = flag0, *nxt = flag1;
+    for (int sweep = 0; sweep < n_nodes + 1; ++sweep) {
         if (threadIdx.x == 0) changed = 0;
         __syncthreads();
         int my_changed = 0;
         for (int u = threadIdx.x; u < n_nodes; u += 256) {
+            if (!cur[u]) continue;
+            cur[u] = 0;
             const unsigned long long dub = *(volatile unsigned long long*)&dist[u];
-            if (dub == kInfBits) continue;
             const double du = __longlong_as_double((long long)dub);
             for (int e = indptr[u]; e < indptr[u + 1]; ++e) {
                 const double nd = __dadd_rn(du, weight[e]);
-                if (nd > limit) continue;
+                if (!(nd <= limit)) continue;
                 const unsigned long long nb = (unsigned long long)__double_as_longlong(nd);
                 const int v = indices[e];
                 if (nb < *(volatile unsigned long long*)&dist[v]) {
-                    if (atomicMin(&dist[v], nb) > nb) my_changed = 1;
+                    if (atomicMin(&dist[v], nb) > nb) { nxt[v] = 1; my_changed = 1; }
+                }
+            }
+        }
+        if (my_changed) changed = 1;
+        __syncthreads();
+        if (!changed) break;
+        uint8_t* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+    }
+    // ---- hop labels over the tight edges (acyclic predecessor choice) ----
+    for (int sweep = 0; sweep < n_nodes + 1; ++sweep) {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        int my_changed = 0;
+        for (int u = threadIdx.x; u < n_nodes; u += 256) {
+            const int hu = *(volatile int32_t*)&hop[u];
+            if (hu == 0x7fffffff) continue;
+            const double du = __longlong_as_double((long long)dist[u]);
+            for (int e = indptr[u]; e < indptr[u + 1]; ++e) {
+                const int v = indices[e];
+                if (v == u) continue;
+                const double nd = __dadd_rn(du, weight[e]);
+                if ((unsigned long long)__double_as_longlong(nd) != dist[v]) continue;   // not tight
+                if (hu + 1 < *(volatile int32_t*)&hop[v]) {
+                    if (atomicMin(&hop[v], hu + 1) > hu + 1) my_changed = 1;
                 }
             }
         }
@@ -58,17 +105,21 @@ __global__ void __launch_bounds__(256) sssp_kernel(int n_nodes, const int32_t* _
         if (!changed) break;
         __syncthreads();
     }
-    // predecessor of v: the node u with fl(dist[u] + w(u, v)) == dist[v] (smallest u on an exact tie)
+    // predecessor of v: the smallest u on a tight edge one hop closer to the origin
     for (int u = threadIdx.x; u < n_nodes; u += 256) {
-        const unsigned long long dub = dist[u];
-        if (dub == kInfBits) continue;
-        const double du = __longlong_as_double((long long)dub);
+        const int hu = hop[u];
+        if (hu == 0x7fffffff) continue;
+        const double du = __longlong_as_double((long long)dist[u]);
         for (int e = indptr[u]; e < indptr[u + 1]; ++e) {
             const int v = indices[e];
-            if (v == src) continue;
+            if (v == src || v == u) continue;
             const double nd = __dadd_rn(du, weight[e]);
-            if ((unsigned long long)__double_as_longlong(nd) == dist[v]) atomicMin(&pred[v], u);
+            if ((unsigned long long)__double_as_longlong(nd) == dist[v] && hu + 1 == hop[v]) atomicMin(&pred[v], u);
         }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int u = threadIdx.x; u < n_nodes; u += 256) dist_g[u] = dist[u];
     }
 }
 
@@ -138,14 +189,17 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
     }
     const int n_edges = indptr[n_nodes];
     const double lim = limit < 0 ? __builtin_inf() : limit;
+    const size_t smem_bytes = (size_t)n_nodes * 14;   // dist 8 + hop 4 + two frontier flags
+    const bool use_smem = smem_bytes <= 200 * 1024;
     // chunk the sources so that dist + pred stay under ~2 GB
-    const size_t per_source = (size_t)n_nodes * 12;
+    const size_t per_source = (size_t)n_nodes * (use_smem ? 12 : 18);
     size_t chunk_sz = ((size_t)2 << 30) / (per_source > 0 ? per_source : 1);
     if (chunk_sz < 1) chunk_sz = 1;
     int chunk = chunk_sz > (size_t)1 << 20 ? 1 << 20 : (int)chunk_sz;
     if (chunk > (int)sources.size()) chunk = (int)sources.size();
     int32_t *d_indptr = nullptr, *d_indices = nullptr, *d_sources = nullptr, *d_pred = nullptr, *d_pair_slot = nullptr,
-            *d_origin = nullptr, *d_dest = nullptr, *d_len = nullptr, *d_nodes = nullptr;
+            *d_origin = nullptr, *d_dest = nullptr, *d_len = nullptr, *d_nodes = nullptr, *d_hop = nullptr;
+    uint8_t* d_flag = nullptr;
     double* d_weight = nullptr;
     unsigned long long* d_dist = nullptr;
     std::vector<int32_t> sel_pairs, sel_slot, sel_o, sel_d, tmp_len, tmp_nodes;
@@ -155,6 +209,12 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
     RCU(cudaMalloc(&d_sources, sizeof(int32_t) * chunk));
     RCU(cudaMalloc(&d_dist, sizeof(unsigned long long) * (size_t)chunk * n_nodes));
     RCU(cudaMalloc(&d_pred, sizeof(int32_t) * (size_t)chunk * n_nodes));
+    if (use_smem) {
+        RCU(cudaFuncSetAttribute(sssp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    } else {
+        RCU(cudaMalloc(&d_hop, sizeof(int32_t) * (size_t)chunk * n_nodes));
+        RCU(cudaMalloc(&d_flag, (size_t)chunk * 2 * n_nodes));
+    }
     RCU(cudaMemcpyAsync(d_indptr, indptr, sizeof(int32_t) * (n_nodes + 1), cudaMemcpyDefault, stream));
     RCU(cudaMemcpyAsync(d_indices, indices, sizeof(int32_t) * n_edges, cudaMemcpyDefault, stream));
     RCU(cudaMemcpyAsync(d_weight, weight, sizeof(double) * n_edges, cudaMemcpyDefault, stream));
@@ -175,7 +235,12 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
             const auto& pairs = by_chunk[c];
             if (pairs.empty()) continue;
             RCU(cudaMemcpyAsync(d_sources, sources.data() + s0, sizeof(int32_t) * ns, cudaMemcpyDefault, stream));
-            sssp_kernel<<<ns, 256, 0, stream>>>(n_nodes, d_indptr, d_indices, d_weight, d_sources, lim, d_dist, d_pred);
+            if (use_smem)
+                sssp_kernel<true><<<ns, 256, smem_bytes, stream>>>(n_nodes, d_indptr, d_indices, d_weight, d_sources, lim, d_dist,
+                                                                   d_pred, nullptr, nullptr);
+            else
+                sssp_kernel<false><<<ns, 256, 0, stream>>>(n_nodes, d_indptr, d_indices, d_weight, d_sources, lim, d_dist,
+                                                           d_pred, d_hop, d_flag);
             RCU(cudaGetLastError());
             const int np = (int)pairs.size();
             sel_slot.resize(np); sel_o.resize(np); sel_d.resize(np);
@@ -203,6 +268,7 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
 done:
     cudaFree(d_indptr); cudaFree(d_indices); cudaFree(d_weight); cudaFree(d_sources); cudaFree(d_dist); cudaFree(d_pred);
     cudaFree(d_pair_slot); cudaFree(d_origin); cudaFree(d_dest); cudaFree(d_len); cudaFree(d_nodes);
+    cudaFree(d_hop); cudaFree(d_flag);
     return rc;
 #undef RCU
 }

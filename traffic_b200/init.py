@@ -93,6 +93,57 @@ def init_random_node_start_location(n, graph, car_id=None, alternate_route=None)
     return cars
 
 
+def find_culdesacs(graph):
+    """``navigation.find_culdesacs`` (``navigation.py:522-531``): nodes with exactly one street, in node order.  The
+    reference asks ``osmnx.stats.count_streets_per_node``; on a graph without OSMnx that is the number of distinct
+    neighbours of the node in the undirected sense."""
+    ids, _, (indptr, indices, _w), _, _ = _graph_arrays(graph)
+    n = len(ids)
+    nb = [set() for _ in range(n)]
+    for u in range(n):
+        for v in indices[indptr[u]:indptr[u + 1]].tolist():
+            if v != u:
+                nb[u].add(v)
+                nb[v].add(u)
+    return [i for i in range(n) if len(nb[i]) == 1]
+
+
+def init_culdesac_start_location(n, graph, car_id=None, alternate_route=None):
+    """``simulation.init_culdesac_start_location`` (``simulation.py:259-326``): car i starts in the i-th cul-de-sac and
+    drives to the (i+1)-th.  Same schema, same ValueError / IndexError behaviour (the reference indexes culdesacs[i + 1],
+    so n == len(culdesacs) raises IndexError there too); all routes come from one batched GPU search."""
+    import pandas as pd
+
+    ids, xy, (indptr, indices, w), _, geom = _graph_arrays(graph)
+    culdesacs = find_culdesacs(graph)
+    if n > len(culdesacs):
+        raise ValueError('Number of cars greater than culdesacs to place them. '
+                         'Choose a number less than {}'.format(len(culdesacs)))
+    origins = np.asarray([culdesacs[i] for i in range(n)], np.int32)
+    dests = np.asarray([culdesacs[i + 1] for i in range(n)], np.int32)     # IndexError when n == len(culdesacs), as upstream
+    path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origins, dests)
+    ptr, pxy = (routing.polylines_with_geometry(xy, path_len, path_nodes, geom) if geom
+                else routing.polylines(xy, path_len, path_nodes))
+    cars_data = []
+    for k in range(n):
+        if path_len[k] < 0:
+            print('No path between {} and {}.'.format(ids[origins[k]], ids[dests[k]]))
+            continue
+        seg = pxy[ptr[k]:ptr[k + 1]]
+        cars_data.append({'object': 'car', 'x': xy[origins[k], 0], 'y': xy[origins[k], 1], 'vx': 0, 'vy': 0,
+                          'route-time': 0, 'origin': ids[origins[k]].item(), 'destination': ids[dests[k]].item(),
+                          'route': [ids[j].item() for j in path_nodes[k, :path_len[k]]],
+                          'xpath': seg[:, 0].tolist(), 'ypath': seg[:, 1].tolist(),
+                          'distance-to-car': 0, 'distance-to-node': 0, 'distance-to-red-light': 0})
+    if alternate_route:
+        cars_data[car_id]['route'], cars_data[car_id]['xpath'], cars_data[car_id]['ypath'] = alternate_route
+    cars = pd.DataFrame(cars_data)
+    axis = graph.axis
+    xbins, ybins = np.arange(axis[0], axis[1], 200), np.arange(axis[2], axis[3], 200)
+    cars['xbin'], cars['ybin'] = pd.Series(np.digitize(cars['x'], xbins)), pd.Series(np.digitize(cars['y'], ybins))
+    return cars
+
+
 def init_traffic_lights(graph, prescale=10):
     import pandas as pd
 

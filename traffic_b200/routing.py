@@ -45,9 +45,13 @@ def shortest_paths(indptr, indices, weights, origin, dest, limit: float | None =
                                C.c_double(-1.0 if limit is None else float(limit)), max_len, p(path_len), p(path_nodes), None)
         if rc != 0:
             raise native.NativeError("tb2_route_paths failed (status %d): %s" % (rc, L.tb2_route_last_error().decode()))
-        if (path_len == -2).any() and max_len < n_nodes:
-            max_len = min(n_nodes, max_len * 4)   # a path did not fit: retry with a longer buffer
-            continue
+        if (path_len == -2).any():
+            if max_len < n_nodes:
+                max_len = min(n_nodes, max_len * 4)   # a path did not fit: retry with a longer buffer
+                continue
+            # a simple path never has more than n_nodes nodes: this is a corrupted predecessor walk, not "no path"
+            raise native.NativeError("tb2_route_paths: predecessor walk exceeded the number of nodes (%d pairs)"
+                                     % int((path_len == -2).sum()))
         return path_len, path_nodes
 
 

@@ -30,7 +30,8 @@ class SynthGraph:
     """
 
     def __init__(self, nx_: int, ny_: int, spacing: float = 100.0, x0: float = 566000.0, y0: float = 4186000.0,
-                 theta_deg: float = 29.0, jitter: float = 5.0, seed: int = 0, node_id_base: int = 1000):
+                 theta_deg: float = 29.0, jitter: float = 5.0, seed: int = 0, node_id_base: int = 1000,
+                 culdesacs: int = 0):
         self.nx, self.ny = int(nx_), int(ny_)
         self.spacing = float(spacing)
         self.node_id_base = int(node_id_base)
@@ -49,11 +50,18 @@ class SynthGraph:
         ry -= ry.min()
         self.node_xy = np.stack([x0 + rx, y0 + ry], axis=1)  # (n, 2) float64
         n = self.nx * self.ny
-        self.node_ids = self.node_id_base + np.arange(n, dtype=np.int64)
         idx = np.arange(n).reshape(self.ny, self.nx)
         right = np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1)
         up = np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()], 1)
         und = np.concatenate([right, up], 0)
+        self.n_culdesacs = int(culdesacs)
+        if culdesacs:   # dead-end stubs (one street each, navigation.find_culdesacs) hanging off random grid nodes
+            host = rng.choice(n, culdesacs, replace=False)
+            ang = rng.uniform(0, 2 * math.pi, culdesacs)
+            stub = self.node_xy[host] + 0.45 * spacing * np.stack([np.cos(ang), np.sin(ang)], 1)
+            self.node_xy = np.concatenate([self.node_xy, stub], 0)
+            und = np.concatenate([und, np.stack([host, n + np.arange(culdesacs)], 1)], 0)
+        self.node_ids = self.node_id_base + np.arange(len(self.node_xy), dtype=np.int64)
         # directed both ways; order: for each undirected edge (u, v) then (v, u)
         self.edge_u = np.concatenate([und[:, 0], und[:, 1]])
         self.edge_v = np.concatenate([und[:, 1], und[:, 0]])
@@ -69,7 +77,7 @@ class SynthGraph:
 
     @property
     def n_nodes(self) -> int:
-        return self.nx * self.ny
+        return len(self.node_xy)
 
     @property
     def G(self):
