@@ -64,7 +64,52 @@ CONFIGS = {
     "dense_dt0.001_p2_s3": dict(g=dict(nx_=12, ny_=12, x0=566000.0, y0=4186000.0, seed=3), n=121, prescale=2, dt=0.001, steps=600, order="lights_cars", seed=3),
     # c2: lower-Manhattan-sized 64x64 grid, 2,000 cars, prescale 10, first 12 steps (the oracle needs ~7 s/step)
     "c2_dt0.001_p10_s0": dict(g=dict(nx_=64, ny_=64, x0=583000.0, y0=4507000.0, seed=0), n=2001, prescale=10, dt=0.001, steps=12, order="lights_cars", seed=0),
+    # hand-built: >= 3 cars in a bin with the two lowest indices off the linspace, two lights in one bin (first all green)
+    "adversarial_dt0.001":  dict(g=dict(nx_=9, ny_=9, x0=566000.0, y0=4186000.0, seed=5), builder="adversarial", dt=0.001, steps=40, order="lights_cars", seed=0),
 }
+
+
+def adversarial_frames(g):
+    """Hand-built frames that pin the first-candidate-only rules of navigation.car_obstacles / light_obstacles
+    (navigation.py:442-452, 474-494) independently of any restatement:
+      * bin A holds cars 0..4: car 2 has car 3 straight ahead on its linspace, but the first other car of the bin in
+        DataFrame order is car 0 (and the next one car 1), both off the linspace -> the reference answers False;
+        car 0 (the bin minimum) looks at car 1, which IS ahead of it -> a distance;
+      * bin A holds two lights: light 0 lies on car 2's linspace with every face green, light 1 behind it has a red
+        anti-parallel face -> the faces of light 0 are exhausted and the distance to light 1 is returned; car 3 has
+        light 0 behind it (off its linspace) -> False at once although light 1 qualifies;
+      * bin B holds car 5 and one all-green light on its linspace -> None."""
+    import pandas as pd
+    ax = g.axis
+    X, Y = ax[0] + 230.0, ax[2] + 230.0          # inside bin (xbin 2, ybin 2)
+    nodes = list(g.G.nodes())
+    def car(x, y, path):
+        return {"object": "car", "x": x, "y": y, "vx": 0, "vy": 0, "route-time": 0, "origin": nodes[0], "destination": nodes[-1],
+                "route": [nodes[0], nodes[-1]], "xpath": [p[0] for p in path], "ypath": [p[1] for p in path],
+                "distance-to-car": 0, "distance-to-node": 0, "distance-to-red-light": 0}
+    cars = [
+        car(X + 10.0, Y + 150.0, [(X + 190.0, Y + 153.0), (X + 420.0, Y + 160.0)]),     # 0: eastbound, top of the bin
+        car(X + 100.0, Y + 151.5, [(X + 190.0, Y + 153.0), (X + 420.0, Y + 160.0)]),    # 1: ahead of car 0
+        car(X + 20.0, Y + 20.0, [(X + 170.0, Y + 100.0), (X + 400.0, Y + 230.0)]),      # 2: diagonal, cars 0/1 off its line
+        car(X + 80.0, Y + 52.0, [(X + 170.0, Y + 100.0), (X + 400.0, Y + 230.0)]),      # 3: straight ahead of car 2
+        car(X + 50.0, Y + 36.0, [(X + 170.0, Y + 100.0), (X + 400.0, Y + 230.0)]),      # 4: between 2 and 3
+        car(X + 240.0, Y + 30.0, [(X + 380.0, Y + 90.0), (X + 600.0, Y + 200.0)]),      # 5: next bin east, all-green light ahead
+    ]
+    def light(x, y, vecs, go, sw):
+        return {"object": "light", "node": nodes[1], "degree": len(vecs), "x": x, "y": y, "switch-counter": 0, "switch-time": sw,
+                "out-xpositions": [x + 0.3 * v[0] for v in vecs], "out-ypositions": [y + 0.3 * v[1] for v in vecs],
+                "out-xvectors": [v[0] for v in vecs], "out-yvectors": [v[1] for v in vecs], "go-values": np.array(go)}
+    d = np.array([150.0, 80.0]) / np.hypot(150.0, 80.0)
+    lights = [
+        light(X + 60.0, Y + 41.0, [(60 * d[0], 60 * d[1]), (-60 * d[0], -60 * d[1]), (-40.0, 45.0)], [True, True, True], 0.0),
+        light(X + 120.0, Y + 73.0, [(50.0, -30.0), (-55 * d[0] + 1.0, -55 * d[1] - 1.5), (55 * d[0], 55 * d[1])], [True, False, True], 0.013),
+        light(X + 310.0, Y + 60.0, [(-70.0, -30.0), (70.0, 30.0)], [True, True], 0.0),
+    ]
+    cars, lights = pd.DataFrame(cars), pd.DataFrame(lights)
+    xb, yb = np.arange(ax[0], ax[1], 200), np.arange(ax[2], ax[3], 200)
+    cars["xbin"], cars["ybin"] = np.digitize(cars["x"], xb), np.digitize(cars["y"], yb)
+    lights["xbin"], lights["ybin"] = np.digitize(lights["x"], xb), np.digitize(lights["y"], yb)
+    return cars, lights
 
 
 def _falsy_encode(values, none_as_negzero=False):
@@ -87,8 +132,11 @@ def run_reference(cfg, verbose=True):
     g = SynthGraph(**cfg["g"])
     random.seed(cfg["seed"])
     t0 = time.time()
-    init_cars = ref_sim.init_random_node_start_location(cfg["n"], g)
-    init_lights = ref_sim.init_traffic_lights(g, prescale=cfg["prescale"])
+    if cfg.get("builder") == "adversarial":
+        init_cars, init_lights = adversarial_frames(g)
+    else:
+        init_cars = ref_sim.init_random_node_start_location(cfg["n"], g)
+        init_lights = ref_sim.init_traffic_lights(g, prescale=cfg["prescale"])
     t_init = time.time() - t0
     cars = ref_cars.Cars(init_state=init_cars, graph=g)
     lights = ref_cars.TrafficLights(light_state=init_lights, graph=g)
