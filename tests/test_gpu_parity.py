@@ -147,6 +147,13 @@ def test_error_paths():
         sim.step(0.1, 1, 0)                           # positions changed, no prepare
     with pytest.raises(native.NativeError):
         native._check(sim.L.tb2_step(sim.h, 0.1, 1, 7, None), "tb2_step")  # bad order
+    # tb2_prepare validates the index arrays it will dereference (no device fault on bad C-ABI input)
+    for field, bad in ((native.CURSOR, np.array([5], np.int32)), (native.PATH_END, np.array([99], np.int32)),
+                       (native.PATH_EFF_END, np.array([2], np.int32))):
+        sim2 = native.DeviceSim(w)
+        sim2.upload(field, bad)
+        with pytest.raises(native.NativeError, match="inconsistent index arrays"):
+            native._check(sim2.L.tb2_prepare(sim2.h, None), "tb2_prepare")
 
 
 def test_properties_at_bench_size():

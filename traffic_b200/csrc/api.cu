@@ -486,6 +486,25 @@ int tb2_prepare(tb2_sim* s, void* stream_) {
     CU(cudaMemsetAsync(s->buf<char>(B_TRIP_TIME), 0, s->lay.bytes[B_TRIP_TIME], stream));
     CU(cudaMemsetAsync(s->buf<char>(B_TRIP_STEP), 0, s->lay.bytes[B_TRIP_STEP], stream));
     s->steps = 0;
+    {   // the index arrays the caller uploaded are dereferenced by every kernel: validate them once, here
+        const tb2_config& c = s->cfg;
+        int* bad_dev = reinterpret_cast<int*>(s->buf<char>(B_DONE));   // (zeroed just above; zeroed again below)
+        launch_validate(c.n_replicas * c.n_cars, (long long)c.n_path_points, c.n_lights, c.n_faces, s->n_cells, c.n_cell_lights,
+                        s->buf<int32_t>(B_CURSOR), s->buf<int32_t>(B_PATH_END), s->buf<int32_t>(B_PATH_EFF_END),
+                        s->buf<int32_t>(B_FACE_PTR), s->buf<int32_t>(B_CELL_LIGHT_PTR), s->buf<int32_t>(B_CELL_LIGHT_IDX),
+                        bad_dev, stream);
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaMemsetAsync(bad_dev, 0, sizeof(int), stream));
+        s->launches++;
+        if (bad) {
+            char m[256];
+            snprintf(m, sizeof m, "tb2_prepare: inconsistent index arrays (mask 0x%x: 1 cursor/path_end range, 2 path_eff_end, "
+                     "4 face_ptr, 8 more than 32767 faces per light or lights per bin, 16 cell_light_ptr, 32 cell_light_idx)", bad);
+            return fail(TB2_ERR_INVALID, m);
+        }
+    }
     if (s->cfg.precision == TB2_F64) {
         StepArgs64 a{};
         fill_args<double>(s, &a);

@@ -148,6 +148,11 @@ int resident_fits(int cars_per_replica, int lights_per_replica, int n_cells, int
 // head point + constants, unit face vectors, bins, and the cell table `cur_table` of the three in tab3 (all reset).
 void launch_prepare(const StepArgs64& a, double2* pt_curv, double2* face_unit, int n_faces, cudaStream_t stream);
 void launch_prepare(const StepArgs32& a, float2* pt_curv, float2* face_unit, int n_faces, cudaStream_t stream);
+// range / monotonicity checks of the caller's index arrays (n_cars etc. are per replica except cursor: all replicas);
+// *bad_dev (device int, zeroed by the caller) receives a bit mask of violated rules
+void launch_validate(int n_cars_total, long long n_points, int n_lights, int n_faces, int n_cells, int n_cell_lights,
+                     const int32_t* cursor, const int32_t* path_end, const int32_t* path_eff_end, const int32_t* face_ptr,
+                     const int32_t* cell_light_ptr, const int32_t* cell_light_idx, int* bad_dev, cudaStream_t stream);
 // re-derive the go words of the CURRENT face-state buffer (after tb2_upload(TB2_FACE_GO) / prepare)
 void launch_rebuild_go_words(int n_lights_total, int lights_per_replica, int faces_per_replica, int n_cells,
                              const int32_t* face_ptr, const uint8_t* go_cur, const int2* light_cellinfo, CellDynT* cell_dyn,

@@ -64,3 +64,16 @@ int resident_fits(int cars_per_replica, int lights_per_replica, int n_cells, int
     const size_t smem = precision_f32 ? tb2k::ResidentLayout<float>::bytes(slots) : tb2k::ResidentLayout<double>::bytes(slots);
     return smem <= 200 * 1024 ? cl : 0;   // the cluster size, 0 = does not fit
 }
+
+void launch_validate(int n_cars_total, long long n_points, int n_lights, int n_faces, int n_cells, int n_cell_lights,
+                     const int32_t* cursor, const int32_t* path_end, const int32_t* path_eff_end, const int32_t* face_ptr,
+                     const int32_t* cell_light_ptr, const int32_t* cell_light_idx, int* bad_dev, cudaStream_t stream) {
+    int n = n_cars_total;
+    if (n_lights > n) n = n_lights;
+    if (n_cells > n) n = n_cells;
+    if (n_cell_lights > n) n = n_cell_lights;
+    if (n < 1) n = 1;
+    tb2k::validate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n_cars_total, n_points, n_lights, n_faces, n_cells, n_cell_lights,
+                                                               cursor, path_end, path_eff_end, face_ptr, cell_light_ptr,
+                                                               cell_light_idx, bad_dev);
+}

@@ -1163,6 +1163,34 @@ __global__ void __launch_bounds__(256) prepare_cells_kernel(int n_cells, const i
     out[c] = r;
 }
 
+// tb2_prepare: the caller-supplied index arrays are dereferenced by every kernel - check them once (bit k of *bad = rule k)
+static __global__ void __launch_bounds__(256) validate_kernel(int n_cars, long long n_points, int n_lights, int n_faces,
+                                                              int n_cells, int n_cell_lights, const int32_t* cursor,
+                                                              const int32_t* path_end, const int32_t* path_eff_end,
+                                                              const int32_t* face_ptr, const int32_t* cell_light_ptr,
+                                                              const int32_t* cell_light_idx, int* bad) {
+    const int k = (int)(blockIdx.x * 256 + threadIdx.x);
+    int b = 0;
+    if (k < n_cars) {
+        const long long c = cursor[k], e = path_end[k], f = path_eff_end[k];
+        if (c < 0 || e < c || e > n_points) b |= 1;            // 0 <= cursor <= path_end <= P
+        if (f < 0 || f > e) b |= 2;                            // path_eff_end <= path_end
+    }
+    if (k < n_lights) {
+        const int f0 = face_ptr[k], f1 = face_ptr[k + 1];
+        if (f0 < 0 || f1 < f0 || f1 > n_faces) b |= 4;         // face_ptr monotone within [0, F]
+        if (f1 - f0 >= 32768) b |= 8;                          // faces per light < 2^15 (go word / cell record fields)
+    }
+    if (k == 0 && n_lights > 0 && (face_ptr[0] != 0 || face_ptr[n_lights] != n_faces)) b |= 4;
+    if (k < n_cells) {
+        const int l0 = cell_light_ptr[k], l1 = cell_light_ptr[k + 1];
+        if (l0 < 0 || l1 < l0 || l1 > n_cell_lights) b |= 16;  // cell_light_ptr monotone within [0, LC]
+        if (l1 - l0 >= 32768) b |= 8;
+    }
+    if (k < n_cell_lights && (cell_light_idx[k] < 0 || cell_light_idx[k] >= n_lights)) b |= 32;
+    if (b) atomicOr(bad, b);
+}
+
 // (stop, free] log table (see log_stop_free)
 static __global__ void build_log_table_kernel(LogEntry* tab, double stop, double free_d) {
     const int k = (int)threadIdx.x;

@@ -60,10 +60,10 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     """Compile the C-ABI library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    if force:
-        subprocess.check_call(["make", "-C", _CSRC, "-s", "-B"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    else:
-        subprocess.check_call(["make", "-C", _CSRC, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run(["make", "-C", _CSRC, "-s"] + (["-B"] if force else []), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise NativeError("building libtraffic_b200.so failed:\n" + r.stdout[-4000:])
     return LIB_PATH
 
 
