@@ -178,6 +178,11 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
                     int32_t* path_len, int32_t* path_nodes, void* stream);
 const char* tb2_route_last_error(void);
 
+/* Builds with -DTB2_DEBUG_BOUNDS check every gather index of the fp64 step kernels before it is dereferenced (the GPU
+ * pool's compute-sanitizer is closed): bit mask of violated rules since the last call; always 0 in regular builds. */
+int tb2_debug_bounds_enabled(void);
+unsigned int tb2_debug_bounds_violations(void);
+
 /* number of kernel launches issued by this sim so far (bench.py's gpu_launches) */
 int64_t tb2_launch_count(const tb2_sim* sim);
 int64_t tb2_step_count(const tb2_sim* sim);

@@ -24,3 +24,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _bounds_check_build(request):
+    """With a -DTB2_DEBUG_BOUNDS library (scripts/gpu_bounds.sh: TB2_LIB=build_variants/lib_bounds.so) every GPU test also
+    asserts that no step kernel was about to dereference an out-of-range index (compute-sanitizer is closed on the pool)."""
+    yield
+    if "gpu" not in request.keywords or not os.environ.get("TB2_LIB"):
+        return
+    try:
+        from traffic_b200 import native
+        L = native.lib()
+    except Exception:
+        return
+    if L.tb2_debug_bounds_enabled():
+        v = L.tb2_debug_bounds_violations()
+        assert v == 0, "bounds rules violated (mask 0x%x) in %s" % (v, request.node.name)

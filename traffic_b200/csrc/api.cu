@@ -698,6 +698,9 @@ int tb2_frame_wait(tb2_sim* s, int32_t faces_only) {
     return TB2_OK;
 }
 
+int tb2_debug_bounds_enabled(void) { return debug_bounds_enabled(); }
+unsigned int tb2_debug_bounds_violations(void) { return debug_bounds_violations(); }
+
 int64_t tb2_launch_count(const tb2_sim* s) { return s ? s->launches : 0; }
 int64_t tb2_step_count(const tb2_sim* s) { return s ? s->steps : 0; }
 

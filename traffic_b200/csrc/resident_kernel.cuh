@@ -190,6 +190,8 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
             own.stat_ptr = cl.map_shared_rank(&s_stat[own.c / CL], own.c % CL);
             const int j = (m.x != i) ? m.x : m.y;
             R2 o = mk2(R(0), R(0));
+            TB2_BOUNDS(own.c >= 0 && own.c < a.g.n_cells, 8);
+            TB2_BOUNDS(j == TB2_EMPTY || (j >= ibase && j < ibase + N && j != i), 9);
             if (j != TB2_EMPTY) {
                 const int jl = j - ibase;
                 o = *cl.map_shared_rank(&s_pos[lp * B + (jl % B)], jl / B);

@@ -130,6 +130,8 @@ struct PersistArgsT {
 using StepArgs64 = StepArgsT<double>;
 using StepArgs32 = StepArgsT<float>;
 
+unsigned int debug_bounds_violations();
+int debug_bounds_enabled();
 int step_block_threads();
 int pipe_block_threads();
 int pipe_ctas_per_sm();

@@ -77,3 +77,23 @@ void launch_validate(int n_cars_total, long long n_points, int n_lights, int n_f
                                                                cursor, path_end, path_eff_end, face_ptr, cell_light_ptr,
                                                                cell_light_idx, bad_dev);
 }
+
+// -DTB2_DEBUG_BOUNDS builds: bit mask of the bounds rules violated since the last call (0 in regular builds)
+unsigned int debug_bounds_violations() {
+#ifdef TB2_DEBUG_BOUNDS
+    unsigned int v = 0, z = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, g_bounds_violations, sizeof v);
+    cudaMemcpyToSymbol(g_bounds_violations, &z, sizeof z);
+    return v;
+#else
+    return 0;
+#endif
+}
+int debug_bounds_enabled() {
+#ifdef TB2_DEBUG_BOUNDS
+    return 1;
+#else
+    return 0;
+#endif
+}

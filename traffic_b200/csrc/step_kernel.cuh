@@ -52,6 +52,16 @@
 #define TB2_PERSIST_MAX_CTAS 16    // one thread-block cluster (16 needs the non-portable-size opt-in)
 #define TB2K_ORDER_LIGHTS_CARS 1
 
+// compute-sanitizer is closed on the GPU pool: the library carries its own bounds checks instead.  A build with
+// -DTB2_DEBUG_BOUNDS records every out-of-range index the step kernels are about to dereference (bit mask in
+// g_bounds_violations, read and reset by tb2_debug_bounds_violations()); scripts/gpu_bounds.sh runs the GPU suite on it.
+#ifdef TB2_DEBUG_BOUNDS
+__device__ unsigned int g_bounds_violations = 0;
+#define TB2_BOUNDS(cond, bit) do { if (!(cond)) atomicOr(&g_bounds_violations, 1u << (bit)); } while (0)
+#else
+#define TB2_BOUNDS(cond, bit) do { } while (0)
+#endif
+
 namespace tb2k {
 
 template <typename R> constexpr bool is_f64 = std::is_same<R, double>::value;
@@ -371,6 +381,7 @@ static __device__ __noinline__ R light_scan_general(const StepArgsT<R>& a, const
     const int lb = a.cell_light_ptr[c], le = a.cell_light_ptr[c + 1];
     for (int q = lb + first; q < le; ++q) {
         const int l = a.cell_light_idx[q];
+        TB2_BOUNDS(l >= 0 && l < a.lights_per_replica, 7);
         const typename real2<R>::type lp = a.light_xy[l];
         if (!(on_axis(ax, 1, lp.x, a.origin_x) && on_axis(ay, 1, lp.y, a.origin_y))) return R(0);
         const R cvx = lp.x - x, cvy = lp.y - y;
@@ -505,6 +516,7 @@ __device__ __forceinline__ bool view_crossed(const StepArgsT<R>& a, typename rea
 // route point, or the destination node when the head was the last one
 template <typename R>
 __device__ __forceinline__ const typename real2<R>::type* crossing_target(const StepArgsT<R>& a, int i, int cur, int end) {
+    TB2_BOUNDS(cur >= 0 && cur < end, 6);
     return (end - cur < 2) ? &a.dest_xy[i] : &a.path_xy[cur + 1];
 }
 // t: the target - the cached head point (head_xy holds the destination once the route is exhausted, written by seg_move /
@@ -710,6 +722,7 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     }
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
+    TB2_BOUNDS(cn >= 0 && cn < a.g.n_cells, 3);
     const int sec = own.sec();
     if (cn != c) own.store_cell(i, cn);
     // (a car that changed bin has no prefetched entry of its new bin: it simply takes the atomics, ~1 % of the cars)
@@ -747,6 +760,8 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     const R2 head = a.head_xy[i];
     const R2 hc = a.head_curv[i];
     const R rt = a.route_time[i];
+    TB2_BOUNDS(c >= 0 && c < a.g.n_cells, 0);
+    TB2_BOUNDS(cur >= 0 && cur <= end && eff <= end, 1);
     // ---- wave 2: the bin's dynamic record (written by the previous step: bypass L1) ----
     const CellDynT* dyn = a.cell_dyn + (cbase + c);
     const int2 m = __ldcg(reinterpret_cast<const int2*>(&dyn->w[2 * rot.tab_cur_k]));
@@ -754,6 +769,7 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     const uint32_t gw = (uint32_t)__ldcg(&dyn->w[TB2_DYN_GO + rot.go_k_cur]);
     // ---- wave 3: candidate leader = first other car of the bin (navigation.py:438-442) ----
     const int j = (m.x != i) ? m.x : m.y;
+    TB2_BOUNDS(j == TB2_EMPTY || (j >= rep * a.cars_per_replica && j < (rep + 1) * a.cars_per_replica && j != i), 2);
     R2 o = mk2(R(0), R(0));
     if (j != TB2_EMPTY) o = __ldcg(&rot.pos_in[j]);
 
@@ -915,6 +931,7 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
     auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
         if (ii < a.n_cars) {
             const int rep = ENS ? ii / a.cars_per_replica : 0;
+            TB2_BOUNDS(sm.cell[s][tid] >= 0 && sm.cell[s][tid] < a.g.n_cells, 4);
             const CellDynT* dyn = a.cell_dyn + (rep * a.g.n_cells + sm.cell[s][tid]);
             cp_async<8>(&sm.m[s][tid], &dyn->w[2 * a.tab_cur_k]);
             cp_async<4>(&sm.sec[s][tid], &dyn->w[2 * a.tab_next_k + 1]);
@@ -931,6 +948,7 @@ __global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kern
         if (ii < a.n_cars) {
             const int2 m = sm.m[s][tid];
             const int j = (m.x != ii) ? m.x : m.y;
+            TB2_BOUNDS(j == TB2_EMPTY || (j >= 0 && j < a.n_cars && j != ii), 5);
             if (j != TB2_EMPTY) cp_async<sizeof(R2)>(&sm.cand[tid], &a.pos_in[j]);
             if (((uint32_t)sm.gw[s][tid]) >> 16) {
                 const char* st = reinterpret_cast<const char*>(&a.cell_stat[sm.cell[s][tid]]);

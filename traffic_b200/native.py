@@ -34,7 +34,7 @@ FIELD_COUNT = 24
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
            "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
            "tb2_launch_count", "tb2_step_count", "tb2_route_paths", "tb2_route_last_error", "tb2_step_host_async",
-           "tb2_frame_wait", "tb2_rollout", "tb2_download_range"]
+           "tb2_frame_wait", "tb2_rollout", "tb2_download_range", "tb2_debug_bounds_enabled", "tb2_debug_bounds_violations"]
 
 
 class Tb2Config(C.Structure):
@@ -87,6 +87,7 @@ def lib():
         L.tb2_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.tb2_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.tb2_download_range.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.tb2_debug_bounds_violations.restype = C.c_uint
         L.tb2_prepare.argtypes = [C.c_void_p, C.c_void_p]
         L.tb2_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
         L.tb2_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
