@@ -17,7 +17,21 @@ __global__ void __launch_bounds__(256) lights_tick_kernel(int n_lights, int ligh
 
 int step_block_threads() { return TB2_BLOCK; }
 int pipe_block_threads() { return TB2_PIPE_BLOCK; }
-int pipe_ctas_per_sm() { return TB2_PIPE_MIN_BLOCKS; }
+int pipe_ctas_per_sm() {
+    // resident CTAs per SM of the pipelined kernel, asked of the occupancy calculator (registers and staging memory
+    // both bound it); cached per process
+    static int cached = -1;
+    if (cached < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tb2k::pipe_kernel<double, false, false>, TB2_PIPE_BLOCK, 0) !=
+                cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = TB2_PIPE_MIN_BLOCKS;
+        }
+        cached = n;
+    }
+    return cached;
+}
 
 void launch_step(const StepArgs64& a, cudaStream_t stream) { tb2k::launch_step_t<double>(a, stream); }
 

@@ -41,7 +41,9 @@
 #ifndef TB2_BLOCK
 #define TB2_BLOCK 128   // threads per CTA of the step kernel (cars per CTA)
 #endif
+#ifndef TB2_PIPE_BLOCK
 #define TB2_PIPE_BLOCK 128         // threads per CTA of the pipelined big-world kernel (cars per tile)
+#endif
 #ifndef TB2_PIPE_MIN_BLOCKS
 #define TB2_PIPE_MIN_BLOCKS 5      // resident CTAs per SM (96 registers per thread, no spills; ~36 KB of staging per CTA)
 #endif
@@ -372,8 +374,8 @@ __device__ __forceinline__ bool red_face_ahead(const StepArgsT<R>& a, const uint
 
 // navigation.light_obstacles (navigation.py:459-498) over the lights first, first+1, ... of bin c through the static
 // cell -> lights CSR: the rare general path (a second light in the bin, or a first light with more than four faces).
-// Returns the distance to the first red anti-parallel face's light, +0 for False (a light off the linspace), -0 for
-// None (lights exhausted).
+// Returns the SQUARED distance to the first red anti-parallel face's light, +0 for False (a light off the linspace), -0
+// for None (lights exhausted).
 template <typename R>
 static __device__ __noinline__ R light_scan_general(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fbase,
                                                     int c, int first, R x, R tx, R y, R ty) {
@@ -385,7 +387,7 @@ static __device__ __noinline__ R light_scan_general(const StepArgsT<R>& a, const
         const typename real2<R>::type lp = a.light_xy[l];
         if (!(on_axis(ax, 1, lp.x, a.origin_x) && on_axis(ay, 1, lp.y, a.origin_y))) return R(0);
         const R cvx = lp.x - x, cvy = lp.y - y;
-        if (red_face_ahead<R>(a, go_cur, a.face_ptr[l], a.face_ptr[l + 1], fbase, cvx, cvy)) return norm2<R>(cvx, cvy);
+        if (red_face_ahead<R>(a, go_cur, a.face_ptr[l], a.face_ptr[l + 1], fbase, cvx, cvy)) return dot2<R>(cvx, cvy, cvx, cvy);
     }
     return -R(0);
 }
@@ -560,12 +562,14 @@ __device__ __forceinline__ Axis<R> axis_of(R start, R stop, R delta, int n) {
 template <typename R, typename Own>
 __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t* __restrict__ go_cur, int fbase, int c,
                                            const View<R>& v, int j, typename real2<R>::type o, uint32_t gw,
-                                           const Own& own, R& d_car, int& lead, R& d_light) {
+                                           const Own& own, R& dd_car, int& lead, R& dd_light) {
     const Axis<R> ax = axis_of<R>(v.x, R(0), v.dx, v.nx), ay = axis_of<R>(v.y, R(0), v.dy, v.ny);
     const int nl = (int)(gw >> 16), nf0 = (int)((gw >> 8) & 0xffu);
-    d_car = R(0);
+    // outputs are SQUARED distances (0 = the reference's False, -0 = None): the one square root a step needs is taken in
+    // seg_move, of the obstacle that counts (sqrt is monotone and correctly rounded, so min-then-sqrt == sqrt-then-min)
+    dd_car = R(0);
     lead = -1;
-    d_light = R(0);
+    dd_light = R(0);
     if (!(v.spaces && (j != TB2_EMPTY || nl))) return;
     // membership of a coordinate in one of the two linspaces (filtered in double mode, plain fp32 in float mode)
     [[maybe_unused]] AxisFilter ffx, ffy;
@@ -580,14 +584,14 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
     };
     if (j != TB2_EMPTY) {
         if (on_x(0, o.x) && on_y(0, o.y)) {
-            d_car = norm2<R>(o.x - v.x, o.y - v.y);
-            if (d_car != R(0)) lead = j;
+            dd_car = dot2<R>(o.x - v.x, o.y - v.y, o.x - v.x, o.y - v.y);
+            if (dd_car != R(0)) lead = j;
         }
     }
     if (nl) {
         if (nf0 > 4) {
             const typename real2<R>::type t = own.target();
-            d_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
+            dd_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
         } else {
             const CellStatT<R> st = own.stat();
             if (on_x(1, st.xy0.x) && on_y(1, st.xy0.y)) {
@@ -608,12 +612,12 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
                     if (is_red && !yes && !no) band |= 1u << k;
                 }
                 if (!found && band) found = first_light_band_exact<R>(a, c, band, cvx, cvy);
-                if (found) d_light = norm2<R>(cvx, cvy);
+                if (found) dd_light = dot2<R>(cvx, cvy, cvx, cvy);
                 else if (nl > 1) {
                     const typename real2<R>::type t = own.target();
-                    d_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, t.x, v.y, t.y);
+                    dd_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, t.x, v.y, t.y);
                 }
-                else d_light = -R(0);   // lights exhausted -> None
+                else dd_light = -R(0);   // lights exhausted -> None
             }
         }
     }
@@ -648,7 +652,7 @@ __device__ __forceinline__ float log_stop_free(const LogEntry*, float d, float, 
 // or deferred by the pipelined kernel).
 template <typename R, bool AUX, bool ENS, typename Own, typename Insert>
 __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& rot, const LogEntry* __restrict__ logtab, int i,
-                                         int rep, const View<R>& v, R d_car, int lead, R d_light, Own& own,
+                                         int rep, const View<R>& v, R dd_car, int lead, R dd_light, Own& own,
                                          Insert insert) {
     using R2 = typename real2<R>::type;
     const int cbase = rep * a.g.n_cells, ibase = rep * a.cars_per_replica;
@@ -666,10 +670,12 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         // point (curvature) or per simulation (obstacle): one log and no division per car, within 4 ulp of the
         // reference's expression.  Pass 0 evaluates the factor the car actually uses (obstacle factor when it has an
         // obstacle, curvature factor otherwise); pass 1 only runs for cars that blend both (models.weigh_factors).
-        const bool c_t = d_car != R(0), r_t = d_light != R(0);  // Python truthiness (NaN truthy)
+        const bool c_t = dd_car != R(0), r_t = dd_light != R(0);  // Python truthiness (NaN truthy)
         const bool obs = c_t || r_t;
-        const bool weigh = c_t && !r_t && d_car > d_node;      // simulation.py:120-126
-        const R d_obs = (c_t && r_t) ? ((d_car <= d_light) ? d_car : d_light) : (c_t ? d_car : d_light);
+        // the obstacle that counts: min(d_car, d_light) when both, else whichever there is (simulation.py:113-131)
+        const R dd_obs = (c_t && r_t) ? ((dd_car <= dd_light) ? dd_car : dd_light) : (c_t ? dd_car : dd_light);
+        const R d_obs = obs ? sqrt(dd_obs) : R(0);
+        const bool weigh = c_t && !r_t && d_obs > d_node;      // simulation.py:120-126 (here d_obs is d_car)
         R r0 = R(1), r1 = R(1);
 #pragma unroll 1
         for (int it = 0; it < 2; ++it) {
@@ -688,13 +694,13 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         }
         R f = r0;   // curvature factor without an obstacle, obstacle factor with one
         // models.weigh_factors (models.py:41-66); d / free as d * (1/free): <= 1 ulp in the argument
-        if (weigh) f = r0 * cos_(d_car * a.inv_free_distance) + r1 * sin_(d_node * a.inv_free_distance);
+        if (weigh) f = r0 * cos_(d_obs * a.inv_free_distance) + r1 * sin_(d_node * a.inv_free_distance);
         f = fabs(f);
         // unit(target - pos) * speed * factor (simulation.py:54-58) with one reciprocal instead of two divisions (<= 1 ulp)
         vx = v.dx * v.inv_d * a.speed_limit * f;
         vy = v.dy * v.inv_d * a.speed_limit * f;
         if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) & isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
-            const bool acc = !r_t && (!c_t || d_car > a.stop_distance);
+            const bool acc = !r_t && (!c_t || d_obs > a.stop_distance);
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
         }
         if (v.crossed) {
@@ -715,8 +721,8 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     if (AUX) {
         a.vel[i] = mk2(vx, vy);
         a.d_node[i] = d_node;
-        a.d_car[i] = d_car;
-        a.d_light[i] = d_light;
+        a.d_car[i] = dd_car != R(0) ? sqrt(dd_car) : R(0);
+        a.d_light[i] = dd_light != R(0) ? sqrt(dd_light) : dd_light;   // keeps +0 (False) / -0 (None)
         a.leader[i] = lead >= 0 ? lead - ibase : -1;
         a.cell_prev[i] = c;
     }
@@ -776,10 +782,10 @@ __device__ __forceinline__ void step_car(const StepArgsT<R>& a, const Rot<R>& ro
     OwnRegs<R> own;
     own.a = &a; own.pos_out = rot.pos_out; own.cur = cur; own.end = end; own.eff = eff; own.c = c; own.sec_ = sec_next; own.hc_ = hc; own.rt_ = rt;
     const View<R> v = seg_view<R>(a, i, p, head, cur, end, eff, own.t);
-    R d_car, d_light;
+    R dd_car, dd_light;
     int lead;
-    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, own, d_car, lead, d_light);
-    seg_move<R, AUX, ENS>(a, rot, logtab, i, rep, v, d_car, lead, d_light, own,
+    seg_detect<R>(a, rot.go_cur, fbase, c, v, j, o, gw, own, dd_car, lead, dd_light);
+    seg_move<R, AUX, ENS>(a, rot, logtab, i, rep, v, dd_car, lead, dd_light, own,
                           [&](int rec, int ii, int sec) { table_insert(&a.cell_dyn[rec].w[2 * rot.tab_next_k], ii, sec); });
 }
 
@@ -895,8 +901,13 @@ struct OwnSmem {
     }
 };
 
+#ifdef TB2_PIPE_MAXNREG
+#define TB2_PIPE_BOUNDS __maxnreg__(TB2_PIPE_MAXNREG)
+#else
+#define TB2_PIPE_BOUNDS __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS)
+#endif
 template <typename R, bool AUX, bool ENS>
-__global__ void __launch_bounds__(TB2_PIPE_BLOCK, TB2_PIPE_MIN_BLOCKS) pipe_kernel(const __grid_constant__ StepArgsT<R> a) {
+__global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R> a) {
     using R2 = typename real2<R>::type;
     constexpr int B = TB2_PIPE_BLOCK;
     __shared__ __align__(16) PipeSmemT<R> sm;
