@@ -36,6 +36,9 @@ struct OwnResident {
     using R2 = typename real2<R>::type;
     const StepArgsT<R>* a;
     R2 p, head, hc_, t;
+    R2 nxt, nxt_hc, dst;   // the route point after the head + its curvature constants, the destination: a crossing step
+                           // (some car of the world crosses in almost every step) must not make its warp the straggler
+                           // of the cluster barrier with a chain of global loads
     R rt_;
     int cur, end, eff, c, sec_;
     R2* pos_out_slot;
@@ -47,7 +50,14 @@ struct OwnResident {
     __device__ __forceinline__ R rt() const { return rt_; }
     __device__ __forceinline__ int cell() const { return c; }
     __device__ __forceinline__ int sec() const { return sec_; }
-    __device__ __forceinline__ R2 next_curv(int q) const { return a->pt_curv[q]; }
+    __device__ __forceinline__ R2 next_curv(int) const { return nxt_hc; }
+    __device__ __forceinline__ R2 dest(int) const { return dst; }
+    __device__ __forceinline__ R2 crossing_target_value() const { return (end - cur < 2) ? dst : nxt; }
+    // issued now, consumed at the next crossing (thousands of cycles away): never waited for
+    __device__ __forceinline__ void load_next() {
+        if (cur + 1 < end) { nxt = a->path_xy[cur + 1]; nxt_hc = a->pt_curv[cur + 1]; }
+    }
+    __device__ __forceinline__ void after_cross(int, int) { load_next(); }
     __device__ __forceinline__ CellStatT<R> stat() const { return *stat_ptr; }
     __device__ __forceinline__ void store_route_time(int, R v) { rt_ = v; }
     __device__ __forceinline__ void store_cursor(int, int v) { cur = v; }
@@ -113,12 +123,15 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
     OwnResident<R> own;
     own.a = &a;
     own.arrived = false;
-    own.p = mk2(R(0), R(0)); own.head = own.p; own.hc_ = own.p; own.t = own.p;
+    own.p = mk2(R(0), R(0)); own.head = own.p; own.hc_ = own.p; own.t = own.p; own.nxt = own.p; own.nxt_hc = own.p; own.dst = own.p;
     own.rt_ = R(0); own.cur = own.end = own.eff = own.c = 0; own.sec_ = TB2_EMPTY;
     if (live) {
         own.p = pa.pos[cp][i];
         own.head = a.head_xy[i]; own.hc_ = a.head_curv[i]; own.rt_ = a.route_time[i];
         own.cur = a.cursor[i]; own.end = a.path_end[i]; own.eff = a.path_eff_end[i]; own.c = a.cell[i];
+        own.dst = a.dest_xy[i];
+        own.nxt = own.dst; own.nxt_hc = own.hc_;
+        own.load_next();
         s_pos[0 * B + tid] = own.p;   // local ping-pong buffer 0 holds the current positions
     }
     // one thread per light keeps the timer state in registers (TrafficLights.update, cars.py:123-133)
@@ -197,7 +210,9 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
                 o = *cl.map_shared_rank(&s_pos[lp * B + (jl % B)], jl / B);
             }
             own.pos_out_slot = &s_pos[(lp ^ 1) * B + tid];
-            const View<R> v = seg_view<R>(a, i, own.p, own.head, own.cur, own.end, own.eff, own.t);
+            const bool crossed = view_crossed<R>(a, own.p, own.head, own.cur, own.eff);
+            own.t = crossed ? own.crossing_target_value() : own.head;
+            const View<R> v = view_build<R>(a, own.p, own.t, own.cur, own.end, own.eff, crossed);
             R d_car, d_light;
             int lead;
             seg_detect<R>(a, rot.go_cur, fbase, own.c, v, j, o, gw, own, d_car, lead, d_light);

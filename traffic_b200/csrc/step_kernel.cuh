@@ -486,6 +486,8 @@ struct OwnRegs {
     __device__ __forceinline__ int cell() const { return c; }
     __device__ __forceinline__ int sec() const { return sec_; }
     __device__ __forceinline__ R2 next_curv(int q) const { return a->pt_curv[q]; }
+    __device__ __forceinline__ R2 dest(int i) const { return a->dest_xy[i]; }
+    __device__ __forceinline__ void after_cross(int, int) {}
     __device__ __forceinline__ CellStatT<R> stat() const { return a->cell_stat[c]; }
     // results go straight to the global columns
     R2* pos_out;
@@ -706,10 +708,11 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         if (v.crossed) {
             const int3 q = own.route();   // (cur, end, eff)
             // new head: the point we just steered to, or the destination once no usable route point is left
-            const R2 nh = (q.x + 1 >= q.z && v.path_len >= 2) ? a.dest_xy[i] : own.target();
+            const R2 nh = (q.x + 1 >= q.z && v.path_len >= 2) ? own.dest(i) : own.target();
             own.store_cursor(i, q.x + 1);
             own.store_head(i, nh);
             if (q.x + 1 < q.y) own.store_head_curv(i, own.next_curv(q.x + 1));
+            own.after_cross(q.x + 1, q.y);
         }
     } else {
         const int3 q = own.route();
@@ -736,7 +739,7 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
     if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
-        const R2 d = a.dest_xy[i];
+        const R2 d = own.dest(i);
         if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
             a.done[rep] = 1;
             a.trip_time[rep] = (double)rt0;
@@ -894,6 +897,8 @@ struct OwnSmem {
     __device__ __forceinline__ int cell() const { return sm->cell[s][tid]; }
     __device__ __forceinline__ int sec() const { return sm->sec[s][tid]; }
     __device__ __forceinline__ R2 next_curv(int) const { return sm->ncurv[tid]; }
+    __device__ __forceinline__ R2 dest(int i) const { return a->dest_xy[i]; }
+    __device__ __forceinline__ void after_cross(int, int) {}
     __device__ __forceinline__ CellStatT<R> stat() const {
         union { CellStatT<R> st; int4 q[2]; } u;
         u.q[0] = sm->st_lo[tid]; u.q[1] = sm->st_hi[tid];
