@@ -43,7 +43,8 @@ def test_frame_stream_equals_animator_pattern_and_golden(k):
         for _ in range(k):
             xy_ref, colors_ref, face_xy_ref = _animator_pattern(a_cars, a_lights, dt)
         xy, go = stream.next()
-        stream.prefetch()
+        if frame < 11:
+            stream.prefetch()                  # the next frame is computed while this one is looked at
         assert np.array_equal(xy, xy_ref), "frame %d" % frame
         assert np.array_equal(go.astype(bool), colors_ref)
         assert np.allclose(stream.face_xy, face_xy_ref, rtol=0, atol=1e-9)
