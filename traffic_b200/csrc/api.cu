@@ -138,6 +138,7 @@ struct tb2_sim {
     bool freeze_done = false;       // inside tb2_rollout: arrived replicas are frozen
     bool go_dirty = false;          // TB2_FACE_GO was uploaded: the per-bin go words must be re-derived before the next step
     bool allow_pipe = true;         // TB2_NO_PIPE=1: big worlds use the plain one-thread-per-car kernel (A/B testing)
+    bool pipe_tma = false;          // TB2_PIPE_TMA=1: own-state columns travel as TMA bulk copies (measured slower, see step_kernel.cuh)
     bool force_pipe = false;        // TB2_FORCE_PIPE=1: every world goes through the pipelined kernel (test coverage)
     int n_sms = 0;
     bool allow_resident = true;     // TB2_NO_RESIDENT=1: small worlds / ensembles use the global-memory kernels (A/B testing)
@@ -289,6 +290,7 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
     a.write_aux = aux;
     // big worlds (at least two tiles per resident CTA): the software-pipelined persistent kernel
     a.pipe_ctas = 0;
+    a.pipe_tma = s->pipe_tma ? 1 : 0;
     if (s->allow_pipe && s->n_sms > 0) {
         const int resident = s->n_sms * pipe_ctas_per_sm();
         const int tiles = (a.n_cars + pipe_block_threads() - 1) / pipe_block_threads();
@@ -386,6 +388,7 @@ int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_s
     if (const char* np = std::getenv("TB2_NO_PIPE")) s->allow_pipe = !(np[0] == '1');
     if (const char* np = std::getenv("TB2_NO_RESIDENT")) s->allow_resident = !(np[0] == '1');
     if (const char* np = std::getenv("TB2_FORCE_PIPE")) s->force_pipe = (np[0] == '1');
+    if (const char* np = std::getenv("TB2_PIPE_TMA")) s->pipe_tma = (np[0] == '1');
     if (s->force_pipe) { s->allow_persistent = false; s->allow_resident = false; }
     {
         int dev = 0;

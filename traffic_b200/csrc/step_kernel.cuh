@@ -862,8 +862,8 @@ struct PipeSmemT {
     R2 pos[2][TB2_PIPE_BLOCK];
     R2 head[2][TB2_PIPE_BLOCK];
     int32_t cur[2][TB2_PIPE_BLOCK], end[2][TB2_PIPE_BLOCK], eff[2][TB2_PIPE_BLOCK], cell[2][TB2_PIPE_BLOCK];
-    R2 hc[TB2_PIPE_BLOCK];
-    R rt[TB2_PIPE_BLOCK];
+    R2 hc[1][TB2_PIPE_BLOCK];
+    R rt[1][TB2_PIPE_BLOCK];
     int2 m[2][TB2_PIPE_BLOCK];
     int32_t sec[2][TB2_PIPE_BLOCK], gw[2][TB2_PIPE_BLOCK];
     R2 cand[TB2_PIPE_BLOCK];
@@ -875,10 +875,10 @@ struct PipeSmemT {
 };
 
 // ... or the thread's staging slots in shared memory (pipelined kernel)
-template <typename R>
-struct OwnSmem {
+template <typename R, typename SM, bool LATE2>
+struct OwnSmemT {
     using R2 = typename real2<R>::type;
-    const PipeSmemT<R>* sm;
+    const SM* sm;
     int s, tid;
     bool crossed;
     const StepArgsT<R>* a;
@@ -892,8 +892,8 @@ struct OwnSmem {
     __device__ __forceinline__ void on_done() {}
     __device__ __forceinline__ R2 target() const { return crossed ? sm->tgt[s][tid] : sm->head[s][tid]; }
     __device__ __forceinline__ int3 route() const { return make_int3(sm->cur[s][tid], sm->end[s][tid], sm->eff[s][tid]); }
-    __device__ __forceinline__ R2 hc() const { return sm->hc[tid]; }
-    __device__ __forceinline__ R rt() const { return sm->rt[tid]; }
+    __device__ __forceinline__ R2 hc() const { if constexpr (LATE2) return sm->hc[s][tid]; else return sm->hc[0][tid]; }
+    __device__ __forceinline__ R rt() const { if constexpr (LATE2) return sm->rt[s][tid]; else return sm->rt[0][tid]; }
     __device__ __forceinline__ int cell() const { return sm->cell[s][tid]; }
     __device__ __forceinline__ int sec() const { return sm->sec[s][tid]; }
     __device__ __forceinline__ R2 next_curv(int) const { return sm->ncurv[tid]; }
@@ -939,8 +939,8 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     };
     auto issue_late = [&](int ii) {
         if (ii < a.n_cars) {
-            cp_async<sizeof(R2)>(&sm.hc[tid], &a.head_curv[ii]);
-            cp_async<sizeof(R)>(&sm.rt[tid], &a.route_time[ii]);
+            cp_async<sizeof(R2)>(&sm.hc[0][tid], &a.head_curv[ii]);
+            cp_async<sizeof(R)>(&sm.rt[0][tid], &a.route_time[ii]);
         }
         cp_async_commit();
     };
@@ -1029,7 +1029,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         View<R> v{};
         // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
         // instead of keeping it in a register across the fp64 sections
-        OwnSmem<R> own{&sm, s, tid, false, &a, rot.pos_out};
+        OwnSmemT<R, PipeSmemT<R>, false> own{&sm, s, tid, false, &a, rot.pos_out};
         if (live) {
             own.crossed = sm.crossed[tid] != 0;
             v = view_build<R>(a, sm.pos[s][tid], own.target(), sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid], own.crossed);
@@ -1060,6 +1060,210 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     }
     finish_insert(i - stride);
     cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA variant of the pipelined kernel (TB2_PIPE_TMA=1 at run time): the own-state columns of a tile travel as 1-D TMA bulk
+// copies (cp.async.bulk.shared.global + mbarrier complete_tx, SASS UBLKCP / SYNCS) - every warp owns its 32-car slice,
+// lane 0 issues eight bulk copies per tile into the warp's slot two tiles ahead, the other lanes only wait on the slot's
+// mbarrier - instead of eight LDGSTS per thread; the data-dependent gathers (bin record, candidate, light record) stay
+// per-thread cp.async.  Bit-identical (tests run it with TB2_PIPE_TMA=1).  Measured: 61 us/step vs 49 us for the LDGSTS
+// form at 1M cars - the warp-level synchronisation and three more live values push the kernel into spilling at 96
+// registers - so it is not the default.
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk, 1-D): one lane moves a whole column segment of a tile, the barrier counts bytes
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TB2_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TB2_DONE_%=;\n"
+        "bra TB2_WAIT_%=;\n"
+        "TB2_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename R>
+struct PipeTmaSmemT {
+    using R2 = typename real2<R>::type;
+    R2 pos[2][TB2_PIPE_BLOCK];
+    R2 head[2][TB2_PIPE_BLOCK];
+    int32_t cur[2][TB2_PIPE_BLOCK], end[2][TB2_PIPE_BLOCK], eff[2][TB2_PIPE_BLOCK], cell[2][TB2_PIPE_BLOCK];
+    R2 hc[2][TB2_PIPE_BLOCK];
+    R rt[2][TB2_PIPE_BLOCK];
+    unsigned long long full[2][TB2_PIPE_BLOCK / 32];   // per warp, per slot: mbarrier "own-state columns of the tile have landed"
+    int2 m[2][TB2_PIPE_BLOCK];
+    int32_t sec[2][TB2_PIPE_BLOCK], gw[2][TB2_PIPE_BLOCK];
+    R2 cand[TB2_PIPE_BLOCK];
+    int4 st_lo[TB2_PIPE_BLOCK], st_hi[TB2_PIPE_BLOCK];
+    R2 tgt[2][TB2_PIPE_BLOCK];
+    R2 ncurv[TB2_PIPE_BLOCK];
+    int32_t crossed[TB2_PIPE_BLOCK];
+    LogEntry logtab[TB2_LOG_N];
+};
+
+template <typename R, bool AUX, bool ENS>
+__global__ void TB2_PIPE_BOUNDS pipe_tma_kernel(const __grid_constant__ StepArgsT<R> a) {
+    using R2 = typename real2<R>::type;
+    constexpr int B = TB2_PIPE_BLOCK;
+    __shared__ __align__(16) PipeTmaSmemT<R> sm;
+    const int tid = (int)threadIdx.x;
+    if ((int)blockIdx.x >= a.pipe_ctas) {   // trailing CTAs: TrafficLights.update
+        const int l = ((int)blockIdx.x - a.pipe_ctas) * B + tid;
+        lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
+                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
+        return;
+    }
+#define stride (a.pipe_ctas * B)   /* re-derived from the constant bank where it is used: one register less to carry */
+    const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
+
+    // Own-state columns of a tile (pos, head point, curvature constants, route time, cursor / end / eff_end / bin): every
+    // warp owns its 32-car slice of the CTA's tile and moves it with EIGHT TMA bulk copies issued by lane 0 into the
+    // warp's slot; the slot's mbarrier counts the bytes.  (Segments are 16-byte multiples; the last, partial tile rounds up
+    // inside the 256-byte padding of the arena's sub-buffers.)  Tiles past the end just arrive.
+    auto produce = [&](int first_of_warp, int s) {
+        if ((tid & 31) != 0) return;
+        const int warp = tid >> 5;
+        unsigned long long* bar = &sm.full[s][warp];
+        int rows = a.n_cars - first_of_warp;
+        rows = rows < 0 ? 0 : (rows > 32 ? 32 : rows);
+        if (rows == 0) { mbar_arrive(bar); return; }
+        const int b2 = (rows * (int)sizeof(R2) + 15) & ~15, b1 = (rows * (int)sizeof(R) + 15) & ~15, b4 = (rows * 4 + 15) & ~15;
+        mbar_expect_tx(bar, 3 * b2 + b1 + 4 * b4);
+        const int o = warp * 32;
+        bulk_g2s(&sm.pos[s][o], &a.pos_in[first_of_warp], b2, bar);
+        bulk_g2s(&sm.head[s][o], &a.head_xy[first_of_warp], b2, bar);
+        bulk_g2s(&sm.hc[s][o], &a.head_curv[first_of_warp], b2, bar);
+        bulk_g2s(&sm.rt[s][o], &a.route_time[first_of_warp], b1, bar);
+        bulk_g2s(&sm.cur[s][o], &a.cursor[first_of_warp], b4, bar);
+        bulk_g2s(&sm.end[s][o], &a.path_end[first_of_warp], b4, bar);
+        bulk_g2s(&sm.eff[s][o], &a.path_eff_end[first_of_warp], b4, bar);
+        bulk_g2s(&sm.cell[s][o], &a.cell[first_of_warp], b4, bar);
+    };
+    auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
+        if (ii < a.n_cars) {
+            const int rep = ENS ? ii / a.cars_per_replica : 0;
+            TB2_BOUNDS(sm.cell[s][tid] >= 0 && sm.cell[s][tid] < a.g.n_cells, 4);
+            const CellDynT* dyn = a.cell_dyn + (rep * a.g.n_cells + sm.cell[s][tid]);
+            cp_async<8>(&sm.m[s][tid], &dyn->w[2 * a.tab_cur_k]);
+            cp_async<4>(&sm.sec[s][tid], &dyn->w[2 * a.tab_next_k + 1]);
+            cp_async<4>(&sm.gw[s][tid], &dyn->w[TB2_DYN_GO + a.go_k_cur]);
+            // a car that crosses its path head this step (~1.5 %) steers to the next route point: fetch it now
+            const int cur = sm.cur[s][tid];
+            const bool crossed = view_crossed<R>(a, sm.pos[s][tid], sm.head[s][tid], cur, sm.eff[s][tid]);
+            sm.crossed[tid] = crossed;
+            if (crossed) cp_async<sizeof(R2)>(&sm.tgt[s][tid], crossing_target<R>(a, ii, cur, sm.end[s][tid]));
+        }
+        cp_async_commit();
+    };
+    auto issue_cand = [&](int ii, int s) {    // needs G2 of that tile
+        if (ii < a.n_cars) {
+            const int2 m = sm.m[s][tid];
+            const int j = (m.x != ii) ? m.x : m.y;
+            TB2_BOUNDS(j == TB2_EMPTY || (j >= 0 && j < a.n_cars && j != ii), 5);
+            if (j != TB2_EMPTY) cp_async<sizeof(R2)>(&sm.cand[tid], &a.pos_in[j]);
+            if (((uint32_t)sm.gw[s][tid]) >> 16) {
+                const char* st = reinterpret_cast<const char*>(&a.cell_stat[sm.cell[s][tid]]);
+                cp_async<16>(&sm.st_lo[tid], st);
+                cp_async<16>(&sm.st_hi[tid], st + 16);
+            }
+            if (sm.crossed[tid]) {
+                const int cur = sm.cur[s][tid];
+                if (cur + 1 < sm.end[s][tid]) cp_async<sizeof(R2)>(&sm.ncurv[tid], &a.pt_curv[cur + 1]);
+            }
+        }
+        cp_async_commit();
+    };
+
+    int i = (int)blockIdx.x * B + tid;
+    // ---- prologue ----
+    const int lane = tid & 31;
+    if (lane == 0) {
+        mbar_init(&sm.full[0][tid >> 5], 1);
+        mbar_init(&sm.full[1][tid >> 5], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    produce(i - lane, 0);
+    produce(i - lane + stride, 1);
+    {   // the log table travels as the first cp.async group (no synchronous load at the head of the kernel)
+        const char* src = reinterpret_cast<const char*>(a.log_table);
+        char* dst = reinterpret_cast<char*>(sm.logtab);
+        for (int k = tid * 16; k < (int)sizeof(sm.logtab); k += B * 16) cp_async<16>(dst + k, src + k);
+        cp_async_commit();
+    }
+    // the reset of the table that the launch after next will fill rides in the shadow of the first HBM round trip
+    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    cp_async_wait<0>();
+    __syncthreads();   // every thread's slice of the log table has landed
+    mbar_wait(&sm.full[0][tid >> 5], 0);
+    issue_dyn(i, 0);
+    cp_async_wait<0>();
+    issue_cand(i, 0);                       // per-thread cp.async groups pending: [G3(0)]
+    // table insertion of the previous tile, second half: the atomicMin that returned `pend_old` is consumed one tile later
+    int pend_rec = -1, pend_old = 0;   // record index of the bin, value the first atomicMin returned
+    auto finish_insert = [&](int ii) {
+        if (pend_rec < 0) return;
+        const int loser = pend_old > ii ? pend_old : ii;   // whoever is not the bin minimum competes for second place
+        if (loser != TB2_EMPTY) atomicMin(&a.cell_dyn[pend_rec].w[2 * a.tab_next_k + 1], loser);
+        pend_rec = -1;
+    };
+    int s = 0;
+    int par = 1;   // bit x: parity of the next phase of slot x's barrier to wait for (slot 0 has been waited for once)
+    for (; i - tid < a.n_cars; i += stride, s ^= 1) {
+        const int rep = ENS ? i / a.cars_per_replica : 0;
+        const bool live = i < a.n_cars && !(ENS && a.freeze_done && a.done[rep]);   // (an arrived rollout is frozen)
+        View<R> v{};
+        // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
+        // instead of keeping it in a register across the fp64 sections
+        OwnSmemT<R, PipeTmaSmemT<R>, true> own{&sm, s, tid, false, &a, rot.pos_out};
+        if (live) {
+            own.crossed = sm.crossed[tid] != 0;
+            v = view_build<R>(a, sm.pos[s][tid], own.target(), sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid], own.crossed);
+        }
+        finish_insert(i - stride);
+        cp_async_wait<0>();                 // G3(k) landed
+        R d_car = R(0), d_light = R(0);
+        int lead = -1;
+        if (live) {
+            const int2 m = sm.m[s][tid];
+            const int j = (m.x != i) ? m.x : m.y;
+            seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
+                          (uint32_t)sm.gw[s][tid], own, d_car, lead, d_light);
+        }
+        mbar_wait(&sm.full[s ^ 1][tid >> 5], (par >> (s ^ 1)) & 1);   // own state of tile k+1 landed
+        par ^= 1 << (s ^ 1);
+        issue_dyn(i + stride, s ^ 1);       // pending: [G2(k+1)]
+        if (live)
+            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, own,
+                                  [&](int rec, int ii, int sec) {
+                                      if (ii > sec) return;
+                                      pend_old = atomicMin(&a.cell_dyn[rec].w[2 * a.tab_next_k], ii);
+                                      pend_rec = rec;
+                                  });
+        __syncwarp();                       // every lane is done with slot s ...
+        produce(i - lane + 2 * stride, s);  // ... which now receives tile k+2
+        cp_async_wait<0>();                 // G2(k+1) landed
+        issue_cand(i + stride, s ^ 1);      // pending: [G3(k+1)]
+    }
+    finish_insert(i - stride);
+    cp_async_wait<0>();
+#undef stride
 }
 
 // Small worlds (<= 4096 cars): ALL steps of a tb2_step batch in ONE launch.  The CTAs form a single thread-block cluster
@@ -1271,6 +1475,16 @@ void launch_step_t(const StepArgsT<R>& a, cudaStream_t stream) {
         const int lb = (a.n_lights + TB2_PIPE_BLOCK - 1) / TB2_PIPE_BLOCK;
         const int light_blocks = a.tick ? (lb > 0 ? lb : 1) : 0;
         const int grid = a.pipe_ctas + light_blocks;
+        if (a.pipe_tma) {   // TMA bulk-copy variant of the same pipeline (TB2_PIPE_TMA=1)
+            if (ens) {
+                if (a.write_aux) pipe_tma_kernel<R, true, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+                else pipe_tma_kernel<R, false, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+            } else {
+                if (a.write_aux) pipe_tma_kernel<R, true, false><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+                else pipe_tma_kernel<R, false, false><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+            }
+            return;
+        }
         if (ens) {
             if (a.write_aux) pipe_kernel<R, true, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
             else pipe_kernel<R, false, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
