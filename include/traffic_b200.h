@@ -177,6 +177,8 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
                     int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit, int32_t max_len,
                     int32_t* path_len, int32_t* path_nodes, void* stream);
 const char* tb2_route_last_error(void);
+/* tb2_route_paths keeps its device workspace between calls (per host thread); this frees it */
+void tb2_route_release(void);
 
 /* Builds with -DTB2_DEBUG_BOUNDS check every gather index of the fp64 step kernels before it is dereferenced (the GPU
  * pool's compute-sanitizer is closed): bit mask of violated rules since the last call; always 0 in regular builds. */

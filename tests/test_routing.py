@@ -155,4 +155,4 @@ def test_routing_throughput_on_the_manhattan_grid():
     el = time.perf_counter() - t0
     assert (path_len >= 1).all()
     print("routing: %d routes over %d distinct origins in %.1f ms = %.0f routes/s" % (len(origin), len(origin), el * 1e3, len(origin) / el))
-    assert len(origin) / el > 20000
+    assert len(origin) / el > 50000

@@ -570,12 +570,11 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
         sync_go_words(s, stream);
         const cudaError_t pe = s->cfg.precision == TB2_F64 ? step_persistent_t<double>(s, dt, n_steps, order, stream)
                                                            : step_persistent_t<float>(s, dt, n_steps, order, stream);
-        if (pe == cudaErrorCooperativeLaunchTooLarge) {   // the device is shared: fall back to one launch per step for good
-            (void)cudaGetLastError();
+        if (pe != cudaSuccess) {   // cooperative launch refused (shared / partitioned device, capacity queried for another
+            (void)cudaGetLastError();   // variant, ...): fall back to one launch per step for good
             s->allow_persistent = false;
             return tb2_step(s, dt, n_steps, order, stream_);
         }
-        CU(pe);
         s->launches++;
         s->cur_pos ^= (n_steps & 1);
         s->cur_tab = (s->cur_tab + n_steps) % 3;

@@ -149,11 +149,41 @@ __global__ void __launch_bounds__(128) extract_paths_kernel(int n_pairs, int n_n
 
 thread_local std::string g_route_err;
 
+// Grow-only device workspace, kept between calls (an initialiser calls tb2_route_paths several times: cars, then one
+// batch per light face set; a dozen cudaMalloc/cudaFree per call cost more than the searches themselves).
+struct RouteWs {
+    void* p[16] = {};
+    size_t cap[16] = {};
+    int dev = -1;
+    void release() {
+        for (int k = 0; k < 16; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
+    }
+};
+thread_local RouteWs g_ws;
+
+cudaError_t ws_get(int k, size_t bytes, void** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (g_ws.dev != dev) { g_ws.release(); g_ws.dev = dev; }
+    if (bytes < 16) bytes = 16;
+    if (g_ws.cap[k] < bytes) {
+        if (g_ws.p[k]) cudaFree(g_ws.p[k]);
+        g_ws.p[k] = nullptr; g_ws.cap[k] = 0;
+        e = cudaMalloc(&g_ws.p[k], bytes + bytes / 4);
+        if (e != cudaSuccess) return e;
+        g_ws.cap[k] = bytes + bytes / 4;
+    }
+    *out = g_ws.p[k];
+    return cudaSuccess;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* tb2_route_last_error(void) { return g_route_err.c_str(); }
+void tb2_route_release(void) { g_ws.release(); }
 
 // CSR graph on node indices 0..n_nodes-1 (host arrays).  For every pair p writes the node sequence origin..destination
 // to path_nodes[p*max_len ...] and its length to path_len[p] (-1: no path, -2: longer than max_len).  `limit` < 0 means
@@ -203,17 +233,17 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
     double* d_weight = nullptr;
     unsigned long long* d_dist = nullptr;
     std::vector<int32_t> sel_pairs, sel_slot, sel_o, sel_d, tmp_len, tmp_nodes;
-    RCU(cudaMalloc(&d_indptr, sizeof(int32_t) * (n_nodes + 1)));
-    RCU(cudaMalloc(&d_indices, sizeof(int32_t) * (n_edges > 0 ? n_edges : 1)));
-    RCU(cudaMalloc(&d_weight, sizeof(double) * (n_edges > 0 ? n_edges : 1)));
-    RCU(cudaMalloc(&d_sources, sizeof(int32_t) * chunk));
-    RCU(cudaMalloc(&d_dist, sizeof(unsigned long long) * (size_t)chunk * n_nodes));
-    RCU(cudaMalloc(&d_pred, sizeof(int32_t) * (size_t)chunk * n_nodes));
+    RCU(ws_get(0, sizeof(int32_t) * (n_nodes + 1), (void**)&d_indptr));
+    RCU(ws_get(1, sizeof(int32_t) * (n_edges > 0 ? n_edges : 1), (void**)&d_indices));
+    RCU(ws_get(2, sizeof(double) * (n_edges > 0 ? n_edges : 1), (void**)&d_weight));
+    RCU(ws_get(3, sizeof(int32_t) * chunk, (void**)&d_sources));
+    RCU(ws_get(4, sizeof(unsigned long long) * (size_t)chunk * n_nodes, (void**)&d_dist));
+    RCU(ws_get(5, sizeof(int32_t) * (size_t)chunk * n_nodes, (void**)&d_pred));
     if (use_smem) {
         RCU(cudaFuncSetAttribute(sssp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     } else {
-        RCU(cudaMalloc(&d_hop, sizeof(int32_t) * (size_t)chunk * n_nodes));
-        RCU(cudaMalloc(&d_flag, (size_t)chunk * 2 * n_nodes));
+        RCU(ws_get(6, sizeof(int32_t) * (size_t)chunk * n_nodes, (void**)&d_hop));
+        RCU(ws_get(7, (size_t)chunk * 2 * n_nodes, (void**)&d_flag));
     }
     RCU(cudaMemcpyAsync(d_indptr, indptr, sizeof(int32_t) * (n_nodes + 1), cudaMemcpyDefault, stream));
     RCU(cudaMemcpyAsync(d_indices, indices, sizeof(int32_t) * n_edges, cudaMemcpyDefault, stream));
@@ -224,11 +254,11 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
         for (int p = 0; p < n_pairs; ++p) by_chunk[pair_slot[p] / chunk].push_back(p);
         size_t max_pairs = 0;
         for (auto& v : by_chunk) max_pairs = v.size() > max_pairs ? v.size() : max_pairs;
-        RCU(cudaMalloc(&d_pair_slot, sizeof(int32_t) * max_pairs));
-        RCU(cudaMalloc(&d_origin, sizeof(int32_t) * max_pairs));
-        RCU(cudaMalloc(&d_dest, sizeof(int32_t) * max_pairs));
-        RCU(cudaMalloc(&d_len, sizeof(int32_t) * max_pairs));
-        RCU(cudaMalloc(&d_nodes, sizeof(int32_t) * max_pairs * (size_t)max_len));
+        RCU(ws_get(8, sizeof(int32_t) * max_pairs, (void**)&d_pair_slot));
+        RCU(ws_get(9, sizeof(int32_t) * max_pairs, (void**)&d_origin));
+        RCU(ws_get(10, sizeof(int32_t) * max_pairs, (void**)&d_dest));
+        RCU(ws_get(11, sizeof(int32_t) * max_pairs, (void**)&d_len));
+        RCU(ws_get(12, sizeof(int32_t) * max_pairs * (size_t)max_len, (void**)&d_nodes));
         for (size_t c = 0; c < by_chunk.size(); ++c) {
             const int s0 = (int)c * chunk;
             const int ns = (int)sources.size() - s0 < chunk ? (int)sources.size() - s0 : chunk;
@@ -266,9 +296,7 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
         }
     }
 done:
-    cudaFree(d_indptr); cudaFree(d_indices); cudaFree(d_weight); cudaFree(d_sources); cudaFree(d_dist); cudaFree(d_pred);
-    cudaFree(d_pair_slot); cudaFree(d_origin); cudaFree(d_dest); cudaFree(d_len); cudaFree(d_nodes);
-    cudaFree(d_hop); cudaFree(d_flag);
+    // (device buffers stay in the thread's workspace for the next call; tb2_route_release() frees them)
     return rc;
 #undef RCU
 }

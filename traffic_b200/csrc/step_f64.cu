@@ -36,7 +36,9 @@ int pipe_ctas_per_sm() {
 void launch_step(const StepArgs64& a, cudaStream_t stream) { tb2k::launch_step_t<double>(a, stream); }
 
 int persistent_max_cars(int precision_f32) {
-    static int cap64 = -1, cap32 = -1;   // the cooperative variant's capacity depends on the device: query once
+    // the cooperative variant's capacity depends on the device and the kernel variant; it is queried once per process for
+    // the current device and only decides which path is TRIED - a refused launch falls back to per-step launches (api.cu)
+    static int cap64 = -1, cap32 = -1;
     const int cluster_cap = TB2_PERSIST_BLOCK * TB2_PERSIST_MAX_CTAS;
     int& cap = precision_f32 ? cap32 : cap64;
     if (cap < 0) cap = precision_f32 ? persistent_grid_capacity_f32() : tb2k::persistent_grid_capacity_t<double>();
