@@ -513,8 +513,12 @@ struct View {
 template <typename R>
 __device__ __forceinline__ bool view_crossed(const StepArgsT<R>& a, typename real2<R>::type p, typename real2<R>::type head,
                                              int cur, int eff) {
-    return (cur < eff) & isclose_abs<R>(head.x, p.x, p.x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
-           isclose_abs<R>(head.y, p.y, p.y + a.origin_y, R(1.0e-5), R(1.0e-8));
+    if constexpr (is_f64<R>)   // absolute coordinates: origin is 0
+        return (cur < eff) & isclose_abs<R>(head.x, p.x, p.x, R(1.0e-5), R(1.0e-8)) &
+               isclose_abs<R>(head.y, p.y, p.y, R(1.0e-5), R(1.0e-8));
+    else
+        return (cur < eff) & isclose_abs<R>(head.x, p.x, p.x + a.origin_x, R(1.0e-5), R(1.0e-8)) &
+               isclose_abs<R>(head.y, p.y, p.y + a.origin_y, R(1.0e-5), R(1.0e-8));
 }
 // where a car that crosses its path head steers next (FrontView.upcoming_node_position, navigation.py:73-89): the next
 // route point, or the destination node when the head was the last one
@@ -537,7 +541,7 @@ __device__ __forceinline__ View<R> view_build(const StepArgsT<R>& a, typename re
     norm2_inv(v.dx, v.dy, v.d_node, v.inv_d);
     const Axis<R> ax = make_axis<R>(v.x, t.x), ay = make_axis<R>(v.y, t.y);
     v.nx = ax.n; v.ny = ay.n;
-    v.spaces = axis_any<R>(ax, a.origin_x) && axis_any<R>(ay, a.origin_y);
+    v.spaces = axis_any<R>(ax, is_f64<R> ? R(0) : a.origin_x) && axis_any<R>(ay, is_f64<R> ? R(0) : a.origin_y);
     return v;
 }
 template <typename R>
@@ -981,16 +985,24 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
 
     // One thread per CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 with
     // bulk prefetches (whole tiles only), so that every cp.async below is an L2 hit.
+    // Warp 0 of each CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 (whole
+    // tiles only), so that every cp.async below is an L2 hit: one prefetch instruction per column, lane l asks for the
+    // l-th 128-byte line of the column's segment.  (The bulk form, cp.async.bulk.prefetch.L2, wants a warp-uniform address;
+    // inside this loop that costs a ten-instruction waterfall per prefetch.)
     auto prefetch_tile_l2 = [&](int first) {
-        if (tid != 0 || first + B > a.n_cars) return;
-        bulk_prefetch_l2(&a.pos_in[first], B * (int)sizeof(R2));
-        bulk_prefetch_l2(&a.head_xy[first], B * (int)sizeof(R2));
-        bulk_prefetch_l2(&a.head_curv[first], B * (int)sizeof(R2));
-        bulk_prefetch_l2(&a.route_time[first], B * (int)sizeof(R));
-        bulk_prefetch_l2(&a.cursor[first], B * 4);
-        bulk_prefetch_l2(&a.path_end[first], B * 4);
-        bulk_prefetch_l2(&a.path_eff_end[first], B * 4);
-        bulk_prefetch_l2(&a.cell[first], B * 4);
+        if ((tid >> 5) != 0 || first + B > a.n_cars) return;
+        const int off = (tid & 31) * 128;
+        auto pf = [&](const void* base, int bytes) {
+            if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + off));
+        };
+        pf(&a.pos_in[first], B * (int)sizeof(R2));
+        pf(&a.head_xy[first], B * (int)sizeof(R2));
+        pf(&a.head_curv[first], B * (int)sizeof(R2));
+        pf(&a.route_time[first], B * (int)sizeof(R));
+        pf(&a.cursor[first], B * 4);
+        pf(&a.path_end[first], B * 4);
+        pf(&a.path_eff_end[first], B * 4);
+        pf(&a.cell[first], B * 4);
     };
 
     int i = (int)blockIdx.x * B + tid;
