@@ -139,6 +139,10 @@ __device__ __forceinline__ bool isclose_abs(R a, R b, R b_abs, R rtol, R atol) {
 template <typename R>
 __device__ __forceinline__ bool isclose_(R a, R b, R rtol, R atol) { return isclose_abs<R>(a, b, b, rtol, atol); }
 
+// isclose(0, b): |0 - b| <= atol + rtol*|b| for finite b (b == 0 satisfies it: no separate equality term)
+template <typename R>
+__device__ __forceinline__ bool isclose0_(R b, R rtol, R atol) { return (fabs(b) <= atol + rtol * fabs(b)) & (bool)isfinite(b); }
+
 template <typename R>
 __device__ __forceinline__ R dot2(R ax, R ay, R bx, R by) { return fma(ay, by, ax * bx); }
 template <typename R>
@@ -216,9 +220,14 @@ __device__ __forceinline__ Axis<R> make_axis(R start, R stop) {
 // `linspace(...).any()`  (navigation.py:437, 473): non-empty and some element non-zero (absolute coordinates)
 template <typename R>
 __device__ __forceinline__ bool axis_any(const Axis<R>& a, R origin) {
-    if (a.n <= 0) return false;
-    if (a.n == 1) return !((R(0) * a.delta + (a.start + origin)) == R(0));
-    return true;
+    // n == 1: the single sample is 0*delta + start; delta is finite here (1 <= |delta| < 2), so in double mode
+    // (origin 0) the sample is zero iff start is
+    if constexpr (is_f64<R>) return (a.n >= 2) | ((a.n == 1) & (a.start != R(0)));
+    else {
+        if (a.n <= 0) return false;
+        if (a.n == 1) return !((R(0) * a.delta + (a.start + origin)) == R(0));
+        return true;
+    }
 }
 // np.isclose(np.linspace(start, stop, n)[kmin:], v, rtol=1e-6).any()   (navigation.py:443-444, 478-479), exact:
 // numpy's samples L_k = k*step + start (L_{n-1} = stop; n == 1: [0*delta + start]; function_base.py:127-175) are
@@ -270,16 +279,45 @@ struct AxisFilter {
     float fs, inv_fs, nm1, tf0, epsc;
     bool ok;
 };
+__device__ __forceinline__ float rcp_approx(float v) {   // one MUFU.RCP (<= 1 ulp); callers pass normal, non-zero values
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float v) {   // one MUFU.RSQ
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ AxisFilter axis_filter(const Axis<double>& a) {
     AxisFilter f;
     f.ok = a.n >= 2 && a.n < 100000;
     const float fd = __double2float_rn(a.delta);
     f.nm1 = (float)(a.n - 1);
-    f.fs = __fdividef(fd, f.nm1);
-    f.inv_fs = __fdividef(f.nm1, fd);
+    // spacing and its reciprocal, each within 2 ulp (f.ok: nm1 >= 1 and |fd| >= 2, so both reciprocals are of normal
+    // numbers); the band below (2e-6 relative to the extent) is 16 ulp wide
+    f.fs = fd * rcp_approx(f.nm1);
+    f.inv_fs = f.nm1 * rcp_approx(fd);
     f.tf0 = __double2float_rn(1.0e-8 + 1.0e-6 * fabs(a.start));
     f.epsc = __fmaf_rn(2.0e-6f, fabsf(fd), 2.5e-3f);
     return f;
+}
+// Outcome of the fp32 filter for one coordinate: `yes` = certainly on the axis, `open` = not certainly off it (yes or
+// undecided).  Branch-free, so that the up to four tests of a car (leader x/y, light x/y) issue back to back.
+struct AxisHit {
+    bool yes, open;
+};
+__device__ __forceinline__ AxisHit on_axis_quick(const Axis<double>& a, const AxisFilter& f, int kmin, double v) {
+    const float w = __double2float_rn(v - a.start);
+    float k = rintf(w * f.inv_fs);
+    k = fminf(fmaxf(k, (float)kmin), f.nm1);              // NaN -> kmin
+    const float r = fabsf(__fmaf_rn(-k, f.fs, w));         // distance to the nearest sample with index in [kmin, n-1]
+    const float eps = __fmaf_rn(2.0e-6f, fabsf(w), f.epsc);
+    const bool some = a.n - kmin > 0;                      // an empty index range is never hit
+    AxisHit h;
+    h.yes = some & f.ok & (r + eps < f.tf0);
+    h.open = some & !(f.ok & (r - eps > f.tf0));           // NaNs stay open: the exact routine decides
+    return h;
 }
 template <typename StopFn>
 __device__ __forceinline__ bool on_axis(const Axis<double>& a, const AxisFilter& f, int kmin, double v, StopFn stop) {
@@ -561,6 +599,28 @@ __device__ __forceinline__ Axis<R> axis_of(R start, R stop, R delta, int n) {
     return ax;
 }
 
+// Filtered anti-parallel test of the bin's first light (static record: snorm16 face units; go bits from the go word):
+// true iff a red face is anti-parallel to the car -> light vector (cvx, cvy).  Faces whose fp32 cosine falls inside the
+// filter band are re-evaluated exactly.
+template <typename R, typename Own>
+__device__ __forceinline__ bool first_light_red_ahead(const StepArgsT<R>& a, int c, const Own& own, uint32_t gw,
+                                                      int nf0, R cvx, R cvy) {
+    const CellStatT<R> st = own.stat();   // (only the face half is used: the position half was fetched by the caller)
+    const float fx = (float)cvx, fy = (float)cvy;
+    const float inv = rsqrt_approx(fx * fx + fy * fy) * (1.0f / 32767.0f);
+    uint32_t yes = 0, open = 0;   // bit k: face k certainly anti-parallel / not certainly not
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float cs = (fx * (float)st.fu[2 * k] + fy * (float)st.fu[2 * k + 1]) * inv;
+        yes |= (cs < (float)K<double>::cosT - TB2_COS_BAND ? 1u : 0u) << k;
+        open |= (cs > (float)K<double>::cosT + TB2_COS_BAND ? 0u : 1u) << k;   // NaN stays open
+    }
+    const uint32_t red = ~gw & ((1u << nf0) - 1u);
+    if (yes & red) return true;
+    const uint32_t band = open & ~yes & red;
+    return band ? first_light_band_exact<R>(a, c, band, cvx, cvy) : false;
+}
+
 // navigation.car_obstacles (navigation.py:422-456) against candidate j at position o, then navigation.light_obstacles
 // (navigation.py:459-498) for a bin whose go word is gw; load_stat() yields the bin's static light record.
 // own: provider of the car's staged operands (OwnRegs / OwnSmem); target() - the car's target point - is only asked for
@@ -577,53 +637,69 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
     lead = -1;
     dd_light = R(0);
     if (!(v.spaces && (j != TB2_EMPTY || nl))) return;
-    // membership of a coordinate in one of the two linspaces (filtered in double mode, plain fp32 in float mode)
-    [[maybe_unused]] AxisFilter ffx, ffy;
-    if constexpr (is_f64<R>) { ffx = axis_filter(ax); ffy = axis_filter(ay); }
-    auto on_x = [&](int kmin, R val) {
-        if constexpr (is_f64<R>) return on_axis(ax, ffx, kmin, val, [&]() { return own.target().x; });
-        else return on_axis(ax, kmin, val, a.origin_x);
-    };
-    auto on_y = [&](int kmin, R val) {
-        if constexpr (is_f64<R>) return on_axis(ay, ffy, kmin, val, [&]() { return own.target().y; });
-        else return on_axis(ay, kmin, val, a.origin_y);
-    };
-    if (j != TB2_EMPTY) {
-        if (on_x(0, o.x) && on_y(0, o.y)) {
+    if constexpr (is_f64<R>) {
+        // Double mode: the four linspace-membership tests of a car - leader x / y (kmin 0), first light x / y (kmin 1) -
+        // run through the fp32 filter back to back, branch-free; the exact routine is called only for a pair that the
+        // filter leaves open (on_axis is pure, so evaluating y although x fails changes nothing).
+        const bool has_j = j != TB2_EMPTY;
+        const bool lite = nl != 0 && nf0 <= 4;   // first light of the bin from the static record
+        typename real2<R>::type lp = mk2(R(0), R(0));   // position of the bin's first light
+        if (lite) lp = own.stat().xy0;
+        const AxisFilter ffx = axis_filter(ax), ffy = axis_filter(ay);
+        const AxisHit cx = on_axis_quick(ax, ffx, 0, o.x), cy = on_axis_quick(ay, ffy, 0, o.y);
+        const AxisHit lx = on_axis_quick(ax, ffx, 1, lp.x), ly = on_axis_quick(ay, ffy, 1, lp.y);
+        bool car_hit = has_j & cx.yes & cy.yes, lit_hit = lite & lx.yes & ly.yes;
+        const bool car_open = has_j & cx.open & cy.open & !car_hit, lit_open = lite & lx.open & ly.open & !lit_hit;
+        if (car_open | lit_open) {   // rare: some coordinate is inside the filter band
+            const typename real2<R>::type t = own.target();
+            if (car_open)
+                car_hit = (cx.yes || on_axis_exact(ax.start, t.x, ax.n, 0, o.x)) &&
+                          (cy.yes || on_axis_exact(ay.start, t.y, ay.n, 0, o.y));
+            if (lit_open)
+                lit_hit = (lx.yes || on_axis_exact(ax.start, t.x, ax.n, 1, lp.x)) &&
+                          (ly.yes || on_axis_exact(ay.start, t.y, ay.n, 1, lp.y));
+        }
+        if (car_hit) {
             dd_car = dot2<R>(o.x - v.x, o.y - v.y, o.x - v.x, o.y - v.y);
             if (dd_car != R(0)) lead = j;
         }
-    }
-    if (nl) {
-        if (nf0 > 4) {
-            const typename real2<R>::type t = own.target();
-            dd_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
-        } else {
-            const CellStatT<R> st = own.stat();
-            if (on_x(1, st.xy0.x) && on_y(1, st.xy0.y)) {
-                // first light of the bin: faces from the static record (snorm16 units), go bits from the go word
-                const R cvx = st.xy0.x - v.x, cvy = st.xy0.y - v.y;
-                const float fx = (float)cvx, fy = (float)cvy;
-                const float inv = rsqrtf(fx * fx + fy * fy) * (1.0f / 32767.0f);
-                const uint32_t red = ~gw & ((1u << nf0) - 1u);
-                bool found = false;
-                uint32_t band = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float cs = (fx * (float)st.fu[2 * k] + fy * (float)st.fu[2 * k + 1]) * inv;
-                    const bool is_red = (red >> k) & 1u;
-                    const bool yes = cs < (float)K<double>::cosT - TB2_COS_BAND;
-                    const bool no = cs > (float)K<double>::cosT + TB2_COS_BAND;
-                    found = found || (is_red && yes);
-                    if (is_red && !yes && !no) band |= 1u << k;
-                }
-                if (!found && band) found = first_light_band_exact<R>(a, c, band, cvx, cvy);
-                if (found) dd_light = dot2<R>(cvx, cvy, cvx, cvy);
+        if (nl) {
+            if (!lite) {
+                const typename real2<R>::type t = own.target();
+                dd_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
+            } else if (lit_hit) {
+                const R cvx = lp.x - v.x, cvy = lp.y - v.y;
+                if (first_light_red_ahead<R>(a, c, own, gw, nf0, cvx, cvy)) dd_light = dot2<R>(cvx, cvy, cvx, cvy);
                 else if (nl > 1) {
                     const typename real2<R>::type t = own.target();
                     dd_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, t.x, v.y, t.y);
                 }
                 else dd_light = -R(0);   // lights exhausted -> None
+            }
+        }
+    } else {
+        // float mode: plain fp32 membership tests
+        if (j != TB2_EMPTY) {
+            if (on_axis(ax, 0, o.x, a.origin_x) && on_axis(ay, 0, o.y, a.origin_y)) {
+                dd_car = dot2<R>(o.x - v.x, o.y - v.y, o.x - v.x, o.y - v.y);
+                if (dd_car != R(0)) lead = j;
+            }
+        }
+        if (nl) {
+            if (nf0 > 4) {
+                const typename real2<R>::type t = own.target();
+                dd_light = light_scan_general<R>(a, go_cur, fbase, c, 0, v.x, t.x, v.y, t.y);
+            } else {
+                const CellStatT<R> st = own.stat();
+                if (on_axis(ax, 1, st.xy0.x, a.origin_x) && on_axis(ay, 1, st.xy0.y, a.origin_y)) {
+                    const R cvx = st.xy0.x - v.x, cvy = st.xy0.y - v.y;
+                    if (first_light_red_ahead<R>(a, c, own, gw, nf0, cvx, cvy)) dd_light = dot2<R>(cvx, cvy, cvx, cvy);
+                    else if (nl > 1) {
+                        const typename real2<R>::type t = own.target();
+                        dd_light = light_scan_general<R>(a, go_cur, fbase, c, 1, v.x, t.x, v.y, t.y);
+                    }
+                    else dd_light = -R(0);   // lights exhausted -> None
+                }
             }
         }
     }
@@ -680,32 +756,29 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         const bool obs = c_t || r_t;
         // the obstacle that counts: min(d_car, d_light) when both, else whichever there is (simulation.py:113-131)
         const R dd_obs = (c_t && r_t) ? ((dd_car <= dd_light) ? dd_car : dd_light) : (c_t ? dd_car : dd_light);
-        const R d_obs = obs ? sqrt(dd_obs) : R(0);
+        // (no obstacle: d_obs is never looked at - feed sqrt a value that stays on its fast path)
+        const R d_obs = sqrt(obs ? dd_obs : R(1));
         const bool weigh = c_t && !r_t && d_obs > d_node;      // simulation.py:120-126 (here d_obs is d_car)
-        R r0 = R(1), r1 = R(1);
-#pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
-            const bool as_obs = (it == 0) && obs;
-            const bool wanted = (it == 0) ? (obs || hc.y != R(0)) : (weigh && hc.y != R(0));
-            const R d = as_obs ? d_obs : d_node;
-            const R log_den = as_obs ? a.log_stop : hc.x;
-            const R inv_L = as_obs ? a.inv_log_free_over_stop : hc.y;
-            R r = R(1);
-            if (wanted) {
-                if (a.stop_distance < d && d <= a.free_distance)
-                    r = (log_stop_free(logtab, d, a.stop_distance, a.log_scale) - log_den) * inv_L;
-                else if (as_obs && d <= a.stop_distance) r = R(0);
-            }
-            if (it == 0) r0 = r; else r1 = r;
+        auto factor = [&](bool as_obs, R d, R log_den, R inv_L) {
+            if (a.stop_distance < d && d <= a.free_distance)
+                return (log_stop_free(logtab, d, a.stop_distance, a.log_scale) - log_den) * inv_L;
+            return (as_obs && d <= a.stop_distance) ? R(0) : R(1);
+        };
+        // the factor the car actually uses: obstacle factor when it has an obstacle, curvature factor otherwise
+        R f = R(1);
+        if (obs || hc.y != R(0))
+            f = factor(obs, obs ? d_obs : d_node, obs ? a.log_stop : hc.x, obs ? a.inv_log_free_over_stop : hc.y);
+        // models.weigh_factors (models.py:41-66) blends it with the curvature factor; d / free as d * (1/free): <= 1 ulp
+        // in the argument
+        if (weigh) {
+            const R r1 = (hc.y != R(0)) ? factor(false, d_node, hc.x, hc.y) : R(1);
+            f = f * cos_(d_obs * a.inv_free_distance) + r1 * sin_(d_node * a.inv_free_distance);
         }
-        R f = r0;   // curvature factor without an obstacle, obstacle factor with one
-        // models.weigh_factors (models.py:41-66); d / free as d * (1/free): <= 1 ulp in the argument
-        if (weigh) f = r0 * cos_(d_obs * a.inv_free_distance) + r1 * sin_(d_node * a.inv_free_distance);
         f = fabs(f);
         // unit(target - pos) * speed * factor (simulation.py:54-58) with one reciprocal instead of two divisions (<= 1 ulp)
         vx = v.dx * v.inv_d * a.speed_limit * f;
         vy = v.dy * v.inv_d * a.speed_limit * f;
-        if (isclose_<R>(R(0), vx, R(1.0e-5), R(0.1)) & isclose_<R>(R(0), vy, R(1.0e-5), R(0.1))) {
+        if (isclose0_<R>(vx, R(1.0e-5), R(0.1)) & isclose0_<R>(vy, R(1.0e-5), R(0.1))) {
             const bool acc = !r_t && (!c_t || d_obs > a.stop_distance);
             if (acc) { vx += a.default_acceleration; vy += a.default_acceleration; }
         }
