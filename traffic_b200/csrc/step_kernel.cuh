@@ -302,21 +302,27 @@ __device__ __forceinline__ AxisFilter axis_filter(const Axis<double>& a) {
     f.epsc = __fmaf_rn(2.0e-6f, fabsf(fd), 2.5e-3f);
     return f;
 }
-// Outcome of the fp32 filter for one coordinate: `yes` = certainly on the axis, `open` = not certainly off it (yes or
-// undecided).  Branch-free, so that the up to four tests of a car (leader x/y, light x/y) issue back to back.
+// Outcome of the fp32 filter for one coordinate of an axis with at least kmin + 1 samples: `yes` = certainly on the axis,
+// `no` = certainly off it, neither = the exact routine decides.  Branch-free, so that the up to four tests of a car
+// (leader x/y, light x/y) issue back to back.  An axis the filter does not apply to (f.ok false) has a NaN spacing:
+// every comparison fails and the coordinate stays undecided; so does a NaN coordinate.
 struct AxisHit {
-    bool yes, open;
+    bool yes, no;
 };
+__device__ __forceinline__ AxisFilter axis_filter_nan(const Axis<double>& a) {
+    AxisFilter f = axis_filter(a);
+    f.fs = f.ok ? f.fs : __int_as_float(0x7fc00000);
+    return f;
+}
 __device__ __forceinline__ AxisHit on_axis_quick(const Axis<double>& a, const AxisFilter& f, int kmin, double v) {
     const float w = __double2float_rn(v - a.start);
     float k = rintf(w * f.inv_fs);
     k = fminf(fmaxf(k, (float)kmin), f.nm1);              // NaN -> kmin
     const float r = fabsf(__fmaf_rn(-k, f.fs, w));         // distance to the nearest sample with index in [kmin, n-1]
     const float eps = __fmaf_rn(2.0e-6f, fabsf(w), f.epsc);
-    const bool some = a.n - kmin > 0;                      // an empty index range is never hit
     AxisHit h;
-    h.yes = some & f.ok & (r + eps < f.tf0);
-    h.open = some & !(f.ok & (r - eps > f.tf0));           // NaNs stay open: the exact routine decides
+    h.yes = r + eps < f.tf0;
+    h.no = r - eps > f.tf0;
     return h;
 }
 template <typename StopFn>
@@ -645,11 +651,14 @@ __device__ __forceinline__ void seg_detect(const StepArgsT<R>& a, const uint8_t*
         const bool lite = nl != 0 && nf0 <= 4;   // first light of the bin from the static record
         typename real2<R>::type lp = mk2(R(0), R(0));   // position of the bin's first light
         if (lite) lp = own.stat().xy0;
-        const AxisFilter ffx = axis_filter(ax), ffy = axis_filter(ay);
+        // v.spaces: both axes have at least one sample, which is all the leader test (kmin 0) needs; the light test
+        // skips the car's own sample (kmin 1): with a single-sample axis it fails (navigation.py:478-479 on an empty slice)
+        const bool lite2 = lite & (min(ax.n, ay.n) >= 2);
+        const AxisFilter ffx = axis_filter_nan(ax), ffy = axis_filter_nan(ay);
         const AxisHit cx = on_axis_quick(ax, ffx, 0, o.x), cy = on_axis_quick(ay, ffy, 0, o.y);
         const AxisHit lx = on_axis_quick(ax, ffx, 1, lp.x), ly = on_axis_quick(ay, ffy, 1, lp.y);
-        bool car_hit = has_j & cx.yes & cy.yes, lit_hit = lite & lx.yes & ly.yes;
-        const bool car_open = has_j & cx.open & cy.open & !car_hit, lit_open = lite & lx.open & ly.open & !lit_hit;
+        bool car_hit = has_j & cx.yes & cy.yes, lit_hit = lite2 & lx.yes & ly.yes;
+        const bool car_open = has_j & !(cx.no | cy.no) & !car_hit, lit_open = lite2 & !(lx.no | ly.no) & !lit_hit;
         if (car_open | lit_open) {   // rare: some coordinate is inside the filter band
             const typename real2<R>::type t = own.target();
             if (car_open)
@@ -941,14 +950,20 @@ struct PipeSmemT {
     int32_t cur[2][TB2_PIPE_BLOCK], end[2][TB2_PIPE_BLOCK], eff[2][TB2_PIPE_BLOCK], cell[2][TB2_PIPE_BLOCK];
     R2 hc[1][TB2_PIPE_BLOCK];
     R rt[1][TB2_PIPE_BLOCK];
-    int2 m[2][TB2_PIPE_BLOCK];
-    int32_t sec[2][TB2_PIPE_BLOCK], gw[2][TB2_PIPE_BLOCK];
+    int4 dyn[2][2][TB2_PIPE_BLOCK];   // [slot][half]: the bin's whole dynamic record (CellDynT) in two 16-byte halves
     R2 cand[TB2_PIPE_BLOCK];
     int4 st_lo[TB2_PIPE_BLOCK], st_hi[TB2_PIPE_BLOCK];   // CellStatT<R> in two 16-byte halves
     R2 tgt[2][TB2_PIPE_BLOCK];     // crossing step: the next target (next route point / destination)
     R2 ncurv[TB2_PIPE_BLOCK];      // crossing step: curvature constants of the next route point
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
+    // word w of the staged record (w = 2k, 2k+1: table k; 6 + k: go word k)
+    __device__ __forceinline__ const int32_t* word(int s, int tid, int w) const {
+        return reinterpret_cast<const int32_t*>(&dyn[s][w >> 2][tid]) + (w & 3);
+    }
+    __device__ __forceinline__ int2 tab_entry(int s, int tid, int k) const { return *reinterpret_cast<const int2*>(word(s, tid, 2 * k)); }
+    __device__ __forceinline__ int sec_next(int s, int tid, int k) const { return *word(s, tid, 2 * k + 1); }
+    __device__ __forceinline__ uint32_t go_word(int s, int tid, int k) const { return (uint32_t)*word(s, tid, TB2_DYN_GO + k); }
 };
 
 // ... or the thread's staging slots in shared memory (pipelined kernel)
@@ -972,7 +987,7 @@ struct OwnSmemT {
     __device__ __forceinline__ R2 hc() const { if constexpr (LATE2) return sm->hc[s][tid]; else return sm->hc[0][tid]; }
     __device__ __forceinline__ R rt() const { if constexpr (LATE2) return sm->rt[s][tid]; else return sm->rt[0][tid]; }
     __device__ __forceinline__ int cell() const { return sm->cell[s][tid]; }
-    __device__ __forceinline__ int sec() const { return sm->sec[s][tid]; }
+    __device__ __forceinline__ int sec() const { return sm->sec_next(s, tid, a->tab_next_k); }
     __device__ __forceinline__ R2 next_curv(int) const { return sm->ncurv[tid]; }
     __device__ __forceinline__ R2 dest(int i) const { return a->dest_xy[i]; }
     __device__ __forceinline__ void after_cross(int, int) {}
@@ -1021,43 +1036,48 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         }
         cp_async_commit();
     };
+    // (shared-memory reads come first in every issue_*: ptxas pads the first LDGSTS after an LDS with three dummy LDS)
     auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
         if (ii < a.n_cars) {
             const int rep = ENS ? ii / a.cars_per_replica : 0;
-            TB2_BOUNDS(sm.cell[s][tid] >= 0 && sm.cell[s][tid] < a.g.n_cells, 4);
-            const CellDynT* dyn = a.cell_dyn + (rep * a.g.n_cells + sm.cell[s][tid]);
-            cp_async<8>(&sm.m[s][tid], &dyn->w[2 * a.tab_cur_k]);
-            cp_async<4>(&sm.sec[s][tid], &dyn->w[2 * a.tab_next_k + 1]);
-            cp_async<4>(&sm.gw[s][tid], &dyn->w[TB2_DYN_GO + a.go_k_cur]);
-            // a car that crosses its path head this step (~1.5 %) steers to the next route point: fetch it now
-            const int cur = sm.cur[s][tid];
+            const int cell = sm.cell[s][tid];
+            TB2_BOUNDS(cell >= 0 && cell < a.g.n_cells, 4);
+            // a car that crosses its path head this step (~1.5 %) steers to the next route point: fetched with the record
+            const int cur = sm.cur[s][tid], end = sm.end[s][tid];
             const bool crossed = view_crossed<R>(a, sm.pos[s][tid], sm.head[s][tid], cur, sm.eff[s][tid]);
             sm.crossed[tid] = crossed;
-            if (crossed) cp_async<sizeof(R2)>(&sm.tgt[s][tid], crossing_target<R>(a, ii, cur, sm.end[s][tid]));
+            // the bin's whole dynamic record (one sector): table entry, next-table entry, go words
+            const char* dyn = reinterpret_cast<const char*>(a.cell_dyn) + ((size_t)(uint32_t)(rep * a.g.n_cells + cell) << 5);
+            cp_async<16>(&sm.dyn[s][0][tid], dyn);
+            cp_async<16>(&sm.dyn[s][1][tid], dyn + 16);
+            if (crossed) cp_async<sizeof(R2)>(&sm.tgt[s][tid], crossing_target<R>(a, ii, cur, end));
         }
         cp_async_commit();
     };
-    auto issue_cand = [&](int ii, int s) {    // needs G2 of that tile
+    // G3 of tile `ii` (needs its G2), G1 of tile `i2` and GL of tile `ii`, committed in the order the loop consumes them
+    auto issue_cand_early_late = [&](int ii, int s, int i2, int s2) {
+        int j = TB2_EMPTY, cell = 0, cur = 0, end = 0;
+        bool has_light = false, crossed = false;
         if (ii < a.n_cars) {
-            const int2 m = sm.m[s][tid];
-            const int j = (m.x != ii) ? m.x : m.y;
+            const int2 m = sm.tab_entry(s, tid, a.tab_cur_k);
+            j = (m.x != ii) ? m.x : m.y;
             TB2_BOUNDS(j == TB2_EMPTY || (j >= 0 && j < a.n_cars && j != ii), 5);
-            if (j != TB2_EMPTY) cp_async<sizeof(R2)>(&sm.cand[tid], &a.pos_in[j]);
-            if (((uint32_t)sm.gw[s][tid]) >> 16) {
-                const char* st = reinterpret_cast<const char*>(&a.cell_stat[sm.cell[s][tid]]);
-                cp_async<16>(&sm.st_lo[tid], st);
-                cp_async<16>(&sm.st_hi[tid], st + 16);
-            }
-            if (sm.crossed[tid]) {
-                const int cur = sm.cur[s][tid];
-                if (cur + 1 < sm.end[s][tid]) cp_async<sizeof(R2)>(&sm.ncurv[tid], &a.pt_curv[cur + 1]);
-            }
+            has_light = (sm.go_word(s, tid, a.go_k_cur) >> 16) != 0;
+            crossed = sm.crossed[tid] != 0;
+            cell = sm.cell[s][tid]; cur = sm.cur[s][tid]; end = sm.end[s][tid];
         }
+        if (j != TB2_EMPTY) cp_async<sizeof(R2)>(&sm.cand[tid], &a.pos_in[j]);
+        if (has_light) {
+            const char* st = reinterpret_cast<const char*>(&a.cell_stat[cell]);
+            cp_async<16>(&sm.st_lo[tid], st);
+            cp_async<16>(&sm.st_hi[tid], st + 16);
+        }
+        if (crossed && cur + 1 < end) cp_async<sizeof(R2)>(&sm.ncurv[tid], &a.pt_curv[cur + 1]);
         cp_async_commit();
+        issue_early(i2, s2);
+        issue_late(ii);
     };
 
-    // One thread per CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 with
-    // bulk prefetches (whole tiles only), so that every cp.async below is an L2 hit.
     // Warp 0 of each CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 (whole
     // tiles only), so that every cp.async below is an L2 hit: one prefetch instruction per column, lane l asks for the
     // l-th 128-byte line of the column's segment.  (The bulk form, cp.async.bulk.prefetch.L2, wants a warp-uniform address;
@@ -1080,7 +1100,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
 
     int i = (int)blockIdx.x * B + tid;
     // ---- prologue: bring tile 0 to the loop invariant.  cp.async groups complete in commit order and wait_group counts
-    // from the youngest, so groups are committed in the order the loop consumes them: pending = [G3(0), G1(1)].
+    // from the youngest, so groups are committed in the order the loop consumes them: pending = [G3(0), G1(1), GL(0)].
     // The first tile's operands are requested before anything else; the log table and the reset of the table that the
     // launch after next will fill ride in the shadow of that first HBM round trip. ----
     {   // the log table travels with the first group (no synchronous load at the head of the kernel)
@@ -1095,23 +1115,24 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     __syncthreads();   // every thread's slice of the log table has landed
     issue_dyn(i, 0);
     cp_async_wait<0>();
-    issue_cand(i, 0);
-    issue_early(i + stride, 1);
+    issue_cand_early_late(i, 0, i + stride, 1);
     // table insertion of the previous tile, second half: the atomicMin that returned `pend_old` is consumed one tile later
     int pend_rec = -1, pend_old = 0;   // record index of the bin, value the first atomicMin returned
+    int32_t* const tab_next = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a.cell_dyn) + (uint32_t)a.tab_next_k * 8u);
     auto finish_insert = [&](int ii) {
         if (pend_rec < 0) return;
         const int loser = pend_old > ii ? pend_old : ii;   // whoever is not the bin minimum competes for second place
-        if (loser != TB2_EMPTY) atomicMin(&a.cell_dyn[pend_rec].w[2 * a.tab_next_k + 1], loser);
+        if (loser != TB2_EMPTY) atomicMin(tab_next + (size_t)(uint32_t)pend_rec * 8u + 1, loser);
         pend_rec = -1;
     };
     int s = 0;
-    for (; i - tid < a.n_cars; i += stride, s ^= 1) {
+    // a single simulation: a thread past the last car has nothing left to do (there is no block-wide barrier in the
+    // loop); an ensemble keeps walking - a later tile may belong to a rollout that is still running
+    for (; ENS ? (i - tid < a.n_cars) : (i < a.n_cars); i += stride, s ^= 1) {
         const int rep = ENS ? i / a.cars_per_replica : 0;
-        const bool live = i < a.n_cars && !(ENS && a.freeze_done && a.done[rep]);   // (an arrived rollout is frozen)
+        const bool live = !ENS || (i < a.n_cars && !(a.freeze_done && a.done[rep]));   // (an arrived rollout is frozen)
         prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
-        issue_late(i);                      // pending: G3(k), G1(k+1), GL(k)
-        View<R> v{};
+        View<R> v{};                        // pending: G3(k), G1(k+1), GL(k)
         // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
         // instead of keeping it in a register across the fp64 sections
         OwnSmemT<R, PipeSmemT<R>, false> own{&sm, s, tid, false, &a, rot.pos_out};
@@ -1124,10 +1145,10 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         R d_car = R(0), d_light = R(0);
         int lead = -1;
         if (live) {
-            const int2 m = sm.m[s][tid];
+            const int2 m = sm.tab_entry(s, tid, a.tab_cur_k);
             const int j = (m.x != i) ? m.x : m.y;
             seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
-                          (uint32_t)sm.gw[s][tid], own, d_car, lead, d_light);
+                          sm.go_word(s, tid, a.go_k_cur), own, d_car, lead, d_light);
         }
         cp_async_wait<1>();                 // G1(k+1) landed
         issue_dyn(i + stride, s ^ 1);       // pending: GL(k), G2(k+1)
@@ -1136,12 +1157,11 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
             seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, own,
                                   [&](int rec, int ii, int sec) {
                                       if (ii > sec) return;
-                                      pend_old = atomicMin(&a.cell_dyn[rec].w[2 * a.tab_next_k], ii);
+                                      pend_old = atomicMin(tab_next + (size_t)(uint32_t)rec * 8u, ii);
                                       pend_rec = rec;
                                   });
         cp_async_wait<0>();                 // G2(k+1) landed
-        issue_cand(i + stride, s ^ 1);
-        issue_early(i + 2 * stride, s);     // pending: G3(k+1), G1(k+2)
+        issue_cand_early_late(i + stride, s ^ 1, i + 2 * stride, s);   // pending: G3(k+1), G1(k+2), GL(k+1)
     }
     finish_insert(i - stride);
     cp_async_wait<0>();
@@ -1199,6 +1219,7 @@ struct PipeTmaSmemT {
     R2 ncurv[TB2_PIPE_BLOCK];
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
+    __device__ __forceinline__ int sec_next(int s, int tid, int) const { return sec[s][tid]; }
 };
 
 template <typename R, bool AUX, bool ENS>
