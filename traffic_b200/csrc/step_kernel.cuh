@@ -178,14 +178,20 @@ __device__ __forceinline__ int digitize_exact(double x, int nb, double e0, doubl
     return k + 1;
 }
 // Filtered predicate: an fp32 estimate of the fractional bin index decides when x is at least 0.4 m (2e-3 bins) away
-// from every edge - the estimate's error is < 1e-4 bins for maps up to ~100 km - and the exact fp64 routine runs only
-// for positions inside that band (or outside the edge range, or non-finite).
+// from every edge (the estimate's error is < 1.3e-3 bins up to 8192 bins); inside that band one comparison with the
+// exact fp64 value of the nearest edge decides; the general exact routine only runs for positions outside the edge
+// range, non-finite ones, or huge maps.
 __device__ __forceinline__ int digitize_(double x, int nb, double e0, double e1, double d, double inv_d, float f_inv_d,
                                          float f_nb1) {
     const float fx = __double2float_rn(x - e0) * f_inv_d;
     const float k = floorf(fx);
     const float fr = fx - k;
-    if (fr > 2.0e-3f && fr < 1.0f - 2.0e-3f && k >= 0.0f && k < f_nb1 && nb < 30000) return (int)k + 1;
+    if (k >= 0.0f && k < f_nb1 && nb <= 8192) {   // (up to 8192 bins the estimate is good to 1.3e-3 bins)
+        if (fr > 2.0e-3f && fr < 1.0f - 2.0e-3f) return (int)k + 1;
+        // inside the band: x lies strictly between the two neighbours of the nearest edge, so that edge alone decides
+        const int ke = (int)k + (fr >= 0.5f ? 1 : 0);
+        return ke + (x >= edge_(ke, e0, e1, d) ? 1 : 0);
+    }
     return digitize_exact(x, nb, e0, e1, d, inv_d);
 }
 // float mode: closed form on the (uniform) local edges
@@ -808,12 +814,14 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     const int c = own.cell();
     own.store_pos(i, mk2(xn, yn));
     if (AUX) {
-        a.vel[i] = mk2(vx, vy);
-        a.d_node[i] = d_node;
-        a.d_car[i] = dd_car != R(0) ? sqrt(dd_car) : R(0);
-        a.d_light[i] = dd_light != R(0) ? sqrt(dd_light) : dd_light;   // keeps +0 (False) / -0 (None)
-        a.leader[i] = lead >= 0 ? lead - ibase : -1;
-        a.cell_prev[i] = c;
+        // observation-only columns: nobody on the device reads them back - streaming stores (evict-first), so that they do
+        // not push the position / bin-record lines the gathers of this and the next launch hit out of L2
+        __stcs(&a.vel[i], mk2(vx, vy));
+        __stcs(&a.d_node[i], d_node);
+        __stcs(&a.d_car[i], dd_car != R(0) ? sqrt(dd_car) : R(0));
+        __stcs(&a.d_light[i], dd_light != R(0) ? sqrt(dd_light) : dd_light);   // keeps +0 (False) / -0 (None)
+        __stcs(&a.leader[i], lead >= 0 ? lead - ibase : -1);
+        __stcs(&a.cell_prev[i], c);
     }
     // ---- bin of the new position + insertion into the next step's table ----
     const int cn = cell_of<R>(a.g, xn, yn);
