@@ -34,6 +34,7 @@
 #include <cooperative_groups.h>
 #include <math_constants.h>
 #include <type_traits>
+#include <cstdlib>
 
 #ifndef TB2_MIN_BLOCKS
 #define TB2_MIN_BLOCKS 8
@@ -950,6 +951,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Programmatic dependent launch (consecutive step launches on one stream): launch_dependents lets the NEXT launch's CTAs
+// become resident as soon as this grid's CTAs retire, so that their launch latency and the part of their prologue that
+// does not depend on this launch (the log table) overlap this grid's tail; griddepcontrol.wait blocks until the previous
+// grid has completed and its memory is visible.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename R>
 struct PipeSmemT {
     using R2 = typename real2<R>::type;
@@ -1017,8 +1025,10 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     constexpr int B = TB2_PIPE_BLOCK;
     __shared__ __align__(16) PipeSmemT<R> sm;
     const int tid = (int)threadIdx.x;
+    griddep_launch_dependents();
     if ((int)blockIdx.x >= a.pipe_ctas) {   // trailing CTAs: TrafficLights.update
         const int l = ((int)blockIdx.x - a.pipe_ctas) * B + tid;
+        griddep_wait();
         lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
                          a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
         return;
@@ -1116,6 +1126,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         char* dst = reinterpret_cast<char*>(sm.logtab);
         for (int k = tid * 16; k < (int)sizeof(sm.logtab); k += B * 16) cp_async<16>(dst + k, src + k);
     }
+    griddep_wait();   // everything below reads what the previous step wrote
     issue_early(i, 0);
     for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
     clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
@@ -1599,12 +1610,20 @@ void launch_step_t(const StepArgsT<R>& a, cudaStream_t stream) {
             }
             return;
         }
+        // launched with programmatic stream serialization (TB2_NO_PDL=1 turns it off): see griddep_wait()
+        static const bool pdl = !(std::getenv("TB2_NO_PDL") && std::getenv("TB2_NO_PDL")[0] == '1');
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TB2_PIPE_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
         if (ens) {
-            if (a.write_aux) pipe_kernel<R, true, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
-            else pipe_kernel<R, false, true><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+            if (a.write_aux) cudaLaunchKernelEx(&cfg, pipe_kernel<R, true, true>, a);
+            else cudaLaunchKernelEx(&cfg, pipe_kernel<R, false, true>, a);
         } else {
-            if (a.write_aux) pipe_kernel<R, true, false><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
-            else pipe_kernel<R, false, false><<<grid, TB2_PIPE_BLOCK, 0, stream>>>(a);
+            if (a.write_aux) cudaLaunchKernelEx(&cfg, pipe_kernel<R, true, false>, a);
+            else cudaLaunchKernelEx(&cfg, pipe_kernel<R, false, false>, a);
         }
         return;
     }
