@@ -90,8 +90,10 @@ __device__ __forceinline__ float log_(float v) { return logf(v); }
 // sin(x + q*pi/2) for the arguments models.weigh_factors feeds it - distances over free_distance, a few radians, never
 // above 1e5: two-constant Cody-Waite reduction (exact product with the 33-bit head of pi/2) and the fdlibm kernel
 // polynomials, <= 1 ulp (2.2e-16 absolute) on [0, 100]; anything else takes libdevice.  ~20 instructions instead of ~45.
+// (rare paths are kept out of line: the pipelined kernel is sensitive to the instruction footprint of its loop)
+static __device__ __noinline__ double trig_libdevice(double x, int q) { return q ? cos(x) : sin(x); }
 __device__ __forceinline__ double sin_quadrant(double x, int q) {
-    if (!(fabs(x) < 1.0e5)) return q ? cos(x) : sin(x);
+    if (!(fabs(x) < 1.0e5)) return trig_libdevice(x, q);
     const double kf = rint(x * 0.6366197723675814);
     double r = fma(-kf, 1.57079632673412561417e+00, x);
     r = fma(-kf, 6.07710050650619224932e-11, r);
@@ -169,7 +171,7 @@ __device__ __forceinline__ double edge_(int k, double e0, double e1, double d) {
     return k == 0 ? e0 : (k == 1 ? e1 : e0 + (double)k * d);
 }
 // exact: the multiply only seeds the search; the two loops compare against the exact edges
-__device__ __forceinline__ int digitize_exact(double x, int nb, double e0, double e1, double d, double inv_d) {
+static __device__ __noinline__ int digitize_exact(double x, int nb, double e0, double e1, double d, double inv_d) {
     if (nb <= 0) return 0;
     if (isnan(x)) return nb;
     const double q = floor((x - e0) * inv_d);
