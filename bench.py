@@ -8,7 +8,7 @@ profile script's order).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measure
   value     vehicle-updates/s with the state resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e       the same metric through the host-buffer C-ABI call tb2_step_host_async: per frame interval, H2D of the
             light-face states from pinned memory, k steps, D2H of the position frame + face states (north_star: frames
-            every k steps); at least 4 frames whatever --steps is
+            every k steps); at least 8 frames whatever --steps is
   roofline  algorithmic bytes per car-step x cars / mean step-kernel duration vs the measured HBM peak
   cpu_baseline  the C oracle port of the reference, one thread, on a bounded sample of the same workload
   small_world   BASELINE configs[1] (2k cars): microseconds per step of the cluster-resident kernel and what bounds it
@@ -352,12 +352,14 @@ def main():
     N = w.n_cars
 
     # ---- device-resident throughput ----
-    sim.step(dt, args.warmup, order)
-    barrier()
+    # (the clock sampler is started BEFORE the warm-up steps, so that the GPU does not sit idle between the warm-up and
+    # the timed region while nvidia-smi spins up)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    barrier()
+    sim.step(dt, args.warmup, order)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sim.launch_count
     barrier()
@@ -384,21 +386,22 @@ def main():
     end = sim.tensor(native.PATH_END)
     stats = torch.stack([rt.mean(), (cur >= end).double().mean()]).to(torch.float32)
 
-    # ---- end to end through the host-buffer C-ABI call: at least 4 frame intervals of k steps, whatever --steps is ----
+    # ---- end to end through the host-buffer C-ABI call: at least 8 frame intervals of k steps, whatever --steps is ----
     k = max(1, args.frame_every)
-    frames = max(4, -(-args.steps // k))
+    frames = max(8, -(-args.steps // k))
     # a FRESH simulation of the same world, warmed up by the same number of steps, so that the end-to-end leg advances
     # through the same phase of the simulation as the device-resident leg (step cost drifts as queues build up)
     del sim
     sim = native.DeviceSim(w, precision=prec, write_aux=True, neighbor_mode=nmode)
-    sim.step(dt, max(args.warmup - k, 0), order)
+    sim.step(dt, max(args.warmup - 2 * (k // 2), 0), order)
     # pinned host buffers, allocated once: light-face states in / out, two position frames (frame f lands while f+1 runs)
     go_in = torch.from_numpy(sim.download(native.FACE_GO).copy()).pin_memory()
     go_out = torch.empty_like(go_in).pin_memory()
     frames_buf = [torch.empty((N, 2), dtype=torch.float64 if prec == native.F64 else torch.float32).pin_memory()
                   for _ in range(2)]
-    sim.step_host_async(dt, k, order, go_in, frames_buf[0], go_out)  # warm
-    sim.frame_wait()
+    for f in range(2):   # warm: both frame buffers go through the copy engine once
+        sim.step_host_async(dt, k // 2, order, go_in, frames_buf[f], go_out)
+        sim.frame_wait()
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
