@@ -975,6 +975,7 @@ struct PipeSmemT {
     R2 ncurv[TB2_PIPE_BLOCK];      // crossing step: curvature constants of the next route point
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
+    int32_t frozen[2][TB2_PIPE_BLOCK];   // ensembles: the car's rollout had already arrived when its tile was requested
     // word w of the staged record (w = 2k, 2k+1: table k; 6 + k: go word k)
     __device__ __forceinline__ const int32_t* word(int s, int tid, int w) const {
         return reinterpret_cast<const int32_t*>(&dyn[s][w >> 2][tid]) + (w & 3);
@@ -1038,7 +1039,17 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     const int stride = a.pipe_ctas * B;
     const Rot<R> rot{a.pos_in, a.pos_out, a.go_cur, a.tab_cur_k, a.tab_next_k, a.go_k_cur, a.step_index};
 
+    // Ensembles: a rollout whose agent has arrived is frozen (tb2_rollout): its cars are neither loaded nor stepped.  The
+    // flag is sampled once, when the tile's own-state columns are requested, and travels with the staging slot; `done` only
+    // ever goes 0 -> 1 and the state of a finished rollout is never looked at again, so a stale 0 merely costs one more
+    // (unobserved) step of that replica's cars.
+    auto slot_frozen = [&](int s) { if constexpr (ENS) return sm.frozen[s][tid] != 0; else return false; };
     auto issue_early = [&](int ii, int s) {
+        if constexpr (ENS) {
+            const bool fz = ii < a.n_cars && a.freeze_done && a.done[ii / a.cars_per_replica];
+            sm.frozen[s][tid] = fz;
+            if (fz) { cp_async_commit(); return; }
+        }
         if (ii < a.n_cars) {
             cp_async<sizeof(R2)>(&sm.pos[s][tid], &a.pos_in[ii]);
             cp_async<sizeof(R2)>(&sm.head[s][tid], &a.head_xy[ii]);
@@ -1049,8 +1060,8 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         }
         cp_async_commit();
     };
-    auto issue_late = [&](int ii) {
-        if (ii < a.n_cars) {
+    auto issue_late = [&](int ii, int s) {
+        if (ii < a.n_cars && !slot_frozen(s)) {
             cp_async<sizeof(R2)>(&sm.hc[0][tid], &a.head_curv[ii]);
             cp_async<sizeof(R)>(&sm.rt[0][tid], &a.route_time[ii]);
         }
@@ -1058,7 +1069,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     };
     // (shared-memory reads come first in every issue_*: ptxas pads the first LDGSTS after an LDS with three dummy LDS)
     auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
-        if (ii < a.n_cars) {
+        if (ii < a.n_cars && !slot_frozen(s)) {
             const int rep = ENS ? ii / a.cars_per_replica : 0;
             const int cell = sm.cell[s][tid];
             TB2_BOUNDS(cell >= 0 && cell < a.g.n_cells, 4);
@@ -1078,7 +1089,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     auto issue_cand_early_late = [&](int ii, int s, int i2, int s2) {
         int j = TB2_EMPTY, cell = 0, cur = 0, end = 0;
         bool has_light = false, crossed = false;
-        if (ii < a.n_cars) {
+        if (ii < a.n_cars && !slot_frozen(s)) {
             const int2 m = sm.tab_entry(s, tid, a.tab_cur_k);
             j = (m.x != ii) ? m.x : m.y;
             TB2_BOUNDS(j == TB2_EMPTY || (j >= 0 && j < a.n_cars && j != ii), 5);
@@ -1095,7 +1106,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         if (crossed && cur + 1 < end) cp_async<sizeof(R2)>(&sm.ncurv[tid], &a.pt_curv[cur + 1]);
         cp_async_commit();
         issue_early(i2, s2);
-        issue_late(ii);
+        issue_late(ii, s);
     };
 
     // Warp 0 of each CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 (whole
@@ -1104,6 +1115,9 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // inside this loop that costs a ten-instruction waterfall per prefetch.)
     auto prefetch_tile_l2 = [&](int first) {
         if ((tid >> 5) != 0 || first + B > a.n_cars) return;
+        if constexpr (ENS) {   // a tile spans at most two rollouts when a rollout has at least B cars
+            if (a.freeze_done && a.done[first / a.cars_per_replica] && a.done[(first + B - 1) / a.cars_per_replica]) return;
+        }
         const int off = (tid & 31) * 128;
         auto pf = [&](const void* base, int bytes) {
             if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + off));
@@ -1151,7 +1165,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // loop); an ensemble keeps walking - a later tile may belong to a rollout that is still running
     for (; ENS ? (i - tid < a.n_cars) : (i < a.n_cars); i += stride, s ^= 1) {
         const int rep = ENS ? i / a.cars_per_replica : 0;
-        const bool live = !ENS || (i < a.n_cars && !(a.freeze_done && a.done[rep]));   // (an arrived rollout is frozen)
+        const bool live = !ENS || (i < a.n_cars && !slot_frozen(s));   // (an arrived rollout is frozen)
         prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
         View<R> v{};                        // pending: G3(k), G1(k+1), GL(k)
         // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
