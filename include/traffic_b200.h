@@ -145,9 +145,12 @@ int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stre
 /* Replica ensembles (tb2_config.n_replicas, agent_car): the rollout loop of environment.Env.step / simulation_step
  * (environment.py:97-173) - every replica advances until its agent satisfies FrontView.end_of_route
  * (navigation.py:113-128, tested before each step) or max_steps is reached (the reference loop has no cap and may never
- * terminate).  One launch: each replica is one thread-block cluster whose world stays on chip; a
- * replica that has arrived leaves the launch and stays frozen in later calls.  Results: TB2_DONE / TB2_TRIP_TIME /
- * TB2_TRIP_STEP.  TB2_ERR_STATE when the world does not fit the on-chip form (<= 4096 cars and lights per replica). */
+ * terminate).  Small ensembles: one launch, each replica is one thread-block cluster whose world
+ * stays on chip and which leaves the launch when its agent has arrived.  Large ensembles: batched per-step launches of
+ * the HBM-streaming kernels; the cars of an arrived replica are no longer loaded or stepped, the done flags are read
+ * back every 256 steps to stop as soon as every rollout is over.  A replica that has arrived stays frozen in later
+ * tb2_rollout calls; the state of its cars is the one of the arrival step (Env.step has returned, environment.py:124)
+ * and is not meant to be stepped further with tb2_step.  Results: TB2_DONE / TB2_TRIP_TIME / TB2_TRIP_STEP. */
 int tb2_rollout(tb2_sim* sim, double dt, int32_t max_steps, int32_t order, void* stream);
 
 /* End-to-end variant with HOST buffers (what Cars.update does for a caller that passes the lights DataFrame and

@@ -976,6 +976,7 @@ struct PipeSmemT {
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
     int32_t frozen[2][TB2_PIPE_BLOCK];   // ensembles: the car's rollout had already arrived when its tile was requested
+    int32_t cprev[2][TB2_PIPE_BLOCK];    // sparse ensembles (self_clear): the bin the car was in one step ago
     // word w of the staged record (w = 2k, 2k+1: table k; 6 + k: go word k)
     __device__ __forceinline__ const int32_t* word(int s, int tid, int w) const {
         return reinterpret_cast<const int32_t*>(&dyn[s][w >> 2][tid]) + (w & 3);
@@ -1057,6 +1058,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
             cp_async<4>(&sm.end[s][tid], &a.path_end[ii]);
             cp_async<4>(&sm.eff[s][tid], &a.path_eff_end[ii]);
             cp_async<4>(&sm.cell[s][tid], &a.cell[ii]);
+            if constexpr (ENS) if (a.self_clear) cp_async<4>(&sm.cprev[s][tid], &a.cell_prev[ii]);
         }
         cp_async_commit();
     };
@@ -1145,7 +1147,13 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     griddep_wait();   // everything below reads what the previous step wrote
     issue_early(i, 0);
     for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
-    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    // Sparse ensembles (thousands of replicas with more bins than cars each): resetting every bin record of every replica
+    // would move as many sectors as the cars' own state.  Instead every car resets the one entry it can have left in the
+    // table being recycled: that table was filled two steps ago with the bins the cars were in ONE step ago - cell_prev,
+    // kept current by this kernel (written only when it changes) - and the entry shares its sector with the record the car
+    // reads anyway.  (All launches of such a simulation take this path, api.cu:self_clear_mode.)
+    if (!(ENS && a.self_clear))
+        clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
     cp_async_wait<0>();
     __syncthreads();   // every thread's slice of the log table has landed
     issue_dyn(i, 0);
@@ -1195,6 +1203,15 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
                                       pend_old = atomicMin(tab_next + (size_t)(uint32_t)rec * 8u, ii);
                                       pend_rec = rec;
                                   });
+        if constexpr (ENS) {
+            if (a.self_clear && live) {
+                const int co = sm.cprev[s][tid], c = sm.cell[s][tid];
+                TB2_BOUNDS(co >= 0 && co < a.g.n_cells, 8);
+                char* rec = reinterpret_cast<char*>(a.cell_dyn) + ((size_t)(uint32_t)(rep * a.g.n_cells + co) << 5);
+                *reinterpret_cast<int2*>(rec + (uint32_t)a.tab_clear_k * 8u) = make_int2(TB2_EMPTY, TB2_EMPTY);
+                if (co != c) a.cell_prev[i] = c;
+            }
+        }
         cp_async_wait<0>();                 // G2(k+1) landed
         issue_cand_early_late(i + stride, s ^ 1, i + 2 * stride, s);   // pending: G3(k+1), G1(k+2), GL(k+1)
     }
