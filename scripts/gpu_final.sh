@@ -4,7 +4,6 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
 TB2_FORCE_PIPE=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_predicates.py tests/test_gpu_fuzz.py tests/test_ensemble.py -m gpu -x -q 2>&1 | tail -2 > gpurun_out/pytest_gpu_forcepipe.log; cat gpurun_out/pytest_gpu_forcepipe.log
-TB2_FORCE_PIPE=1 TB2_SELF_CLEAR=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_ensemble.py -m gpu -x -q 2>&1 | tail -2 > gpurun_out/pytest_gpu_forcepipe_selfclear.log; cat gpurun_out/pytest_gpu_forcepipe_selfclear.log
 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_driver_settings.json 2> gpurun_out/bench_driver_settings.err
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err

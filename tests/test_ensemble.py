@@ -177,38 +177,6 @@ def test_rollout_batched_form_equals_cluster_resident_form(monkeypatch):
     assert np.array_equal(a[:, 1:], b[:, 1:]) and np.allclose(a[:, 0], b[:, 0], rtol=0, atol=1e-12)
 
 
-@pytest.mark.gpu
-def test_self_clearing_tables_equal_whole_table_reset(monkeypatch):
-    """Sparse ensembles (BASELINE configs[4]: more bins than cars per replica) run the pipelined kernel with self-clearing
-    bin tables - every car resets the entry of the bin it was in one step ago instead of a whole-table reset per step.
-    Forced here on a small ensemble (TB2_FORCE_PIPE=1, TB2_SELF_CLEAR=1), it must leave every replica in exactly the state
-    the whole-table reset leaves it in, and a rollout with frozen replicas on top must report the same trips."""
-    from traffic_b200 import native, synth
-
-    w0, _ = synth.make_city(nx_=32, ny_=32, n_cars=1500, prescale=3, seed=21, max_hops=6)
-    dt, R = 1e-3, 5
-    lens = w0.path_end - w0.path_start
-    agent = int(np.flatnonzero((lens >= 1) & (lens <= 2))[0])
-    fields = (native.POS, native.VEL, native.ROUTE_TIME, native.CURSOR, native.D_NODE, native.D_CAR, native.D_LIGHT,
-              native.CELL, native.LEADER)
-    outs = []
-    monkeypatch.setenv("TB2_FORCE_PIPE", "1")
-    for sc in ("0", "1"):
-        monkeypatch.setenv("TB2_SELF_CLEAR", sc)
-        ens = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
-        snaps = []
-        for n in (1, 2, 298):   # 301 steps in uneven batches: the three tables are recycled out of phase with the batches
-            ens.sim.step(dt, n, native.ORDER_LIGHTS_CARS)
-            snaps.append({f: ens.sim.download(f).copy() for f in fields})
-        outs.append((snaps, ens.rollout(dt, 300)))
-    (sa, ra), (sb, rb) = outs
-    assert (sa[-1][native.LEADER] >= 0).sum() > 50, "test world: hardly any leaders, the tables are not exercised"
-    for a, b in zip(sa, sb):
-        for f in fields:
-            assert np.array_equal(a[f], b[f], equal_nan=True), "field %d differs" % f
-    assert ra[:, 2].sum() >= 1 and np.array_equal(ra, rb, equal_nan=True)
-
-
 def test_reward_matches_the_reference_env_step_fixture():
     """ensemble.reward / rewards_of against (reward, done) recorded from the unmodified reference's Env.step
     (oracle/ref_env_rewards.py -> tests/golden/env_rewards.json)."""

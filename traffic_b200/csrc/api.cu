@@ -136,8 +136,6 @@ struct tb2_sim {
     int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
     bool freeze_done = false;       // inside tb2_rollout: arrived replicas are frozen
-    bool self_clear = false;        // decided by tb2_prepare: sparse ensemble that only ever runs the pipelined kernel
-    int self_clear_env = -1;        // TB2_SELF_CLEAR=0/1: never / whenever the pipelined ensemble kernel is the only path
     bool go_dirty = false;          // TB2_FACE_GO was uploaded: the per-bin go words must be re-derived before the next step
     bool allow_pipe = true;         // TB2_NO_PIPE=1: big worlds use the plain one-thread-per-car kernel (A/B testing)
     bool pipe_tma = false;          // TB2_PIPE_TMA=1: own-state columns travel as TMA bulk copies (measured slower, see step_kernel.cuh)
@@ -301,7 +299,6 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
     }
     a.skip_insert = s->cfg.neighbor_mode == TB2_NEIGHBOR_SORT;
     a.freeze_done = s->freeze_done ? 1 : 0;
-    a.self_clear = (s->self_clear && a.pipe_ctas > 0) ? 1 : 0;
     launch_step(a, stream);
     if (a.skip_insert)   // north_star's pipeline: radix sort by bin + segment heads -> the same table
         s->launches += neighbor_sort_build(a.n_cars, a.cars_per_replica, s->n_cells, key_bits_of(s->cfg), a.cell,
@@ -316,7 +313,6 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
 bool resident_ok(const tb2_sim* s) {
     if (!(s->allow_resident && s->allow_persistent && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC && s->cfg.n_cars > 0))
         return false;
-    if (s->self_clear) return false;
     const int cl = resident_fits(s->cfg.n_cars, s->cfg.n_lights, s->n_cells, s->cfg.precision == TB2_F32);
     if (cl <= 0) return false;
     const int sms = s->n_sms > 0 ? s->n_sms : 1;
@@ -324,21 +320,6 @@ bool resident_ok(const tb2_sim* s) {
     const double waves = (double)((ctas + sms - 1) / sms);
     const double batched_us = std::fmax(10.0, 50.0e-6 * (double)s->cfg.n_cars * s->cfg.n_replicas);
     return waves * 6.0 <= batched_us;
-}
-
-// Self-clearing bin tables (pipe_kernel): only for a replica ensemble whose every launch is the pipelined kernel - the
-// invariant "cell_prev == the bin one step ago" is kept by that kernel alone - and only where it pays: more bin records
-// than a quarter of the cars (BASELINE configs[4]: 4,096 bins for 2,000 cars per replica).
-bool self_clear_mode(const tb2_sim* s) {
-    const tb2_config& c = s->cfg;
-    const bool ens = c.n_replicas > 1 || c.agent_car >= 0;
-    if (!ens || c.neighbor_mode != TB2_NEIGHBOR_ATOMIC || s->pipe_tma || s->self_clear_env == 0 || s->n_sms <= 0) return false;
-    const int64_t cars = (int64_t)c.n_cars * c.n_replicas, records = (int64_t)s->n_cells * c.n_replicas;
-    const int64_t tiles = (cars + pipe_block_threads() - 1) / pipe_block_threads();
-    const bool pipe_always = s->force_pipe ? tiles > 0 : (s->allow_pipe && tiles >= 2 * (int64_t)s->n_sms * pipe_ctas_per_sm());
-    if (!pipe_always || resident_ok(s)) return false;
-    if (s->allow_persistent && cars <= persistent_max_cars(c.precision == TB2_F32)) return false;
-    return s->self_clear_env == 1 || records * 4 >= cars;
 }
 
 // All n_steps of a batch in one launch of the persistent cluster kernel (small worlds only).
@@ -408,7 +389,6 @@ int tb2_create(const tb2_config* cfg, void* arena_dev, size_t arena_bytes, tb2_s
     if (const char* np = std::getenv("TB2_NO_RESIDENT")) s->allow_resident = !(np[0] == '1');
     if (const char* np = std::getenv("TB2_FORCE_PIPE")) s->force_pipe = (np[0] == '1');
     if (const char* np = std::getenv("TB2_PIPE_TMA")) s->pipe_tma = (np[0] == '1');
-    if (const char* np = std::getenv("TB2_SELF_CLEAR")) s->self_clear_env = (np[0] == '1') ? 1 : 0;
     if (s->force_pipe) { s->allow_persistent = false; s->allow_resident = false; }
     {
         int dev = 0;
@@ -540,8 +520,6 @@ int tb2_prepare(tb2_sim* s, void* stream_) {
     s->launches += 3 + (s->cfg.n_cars > 0 ? 2 : 0) + (s->cfg.n_faces > 0 ? 1 : 0) + (s->cfg.n_lights > 0 ? 2 : 0);
     CU(cudaGetLastError());
     s->go_dirty = false;
-    s->self_clear = false;
-    s->self_clear = self_clear_mode(s);   // (prepare left cell_prev == cell and all three tables consistent)
     s->prepared = true;
     return TB2_OK;
 }
@@ -586,7 +564,7 @@ int tb2_step(tb2_sim* s, double dt, int32_t n_steps, int32_t order, void* stream
         CU(cudaGetLastError());
         return TB2_OK;
     }
-    if (s->allow_persistent && !s->self_clear && n_steps >= 2 && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC &&
+    if (s->allow_persistent && n_steps >= 2 && s->cfg.neighbor_mode == TB2_NEIGHBOR_ATOMIC &&
         (int64_t)s->cfg.n_cars * s->cfg.n_replicas <= persistent_max_cars(s->cfg.precision == TB2_F32)) {
         // small world: the whole batch is one launch of the persistent cluster kernel
         sync_go_words(s, stream);

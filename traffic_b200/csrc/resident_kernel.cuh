@@ -50,6 +50,7 @@ struct OwnResident {
     __device__ __forceinline__ R rt() const { return rt_; }
     __device__ __forceinline__ int cell() const { return c; }
     __device__ __forceinline__ int sec() const { return sec_; }
+    __device__ __forceinline__ int rep(int r) const { return r; }
     __device__ __forceinline__ R2 next_curv(int) const { return nxt_hc; }
     __device__ __forceinline__ R2 dest(int) const { return dst; }
     __device__ __forceinline__ R2 crossing_target_value() const { return (end - cur < 2) ? dst : nxt; }

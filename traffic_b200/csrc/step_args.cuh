@@ -61,8 +61,6 @@ struct StepArgsT {
     int32_t agent_car, step_index;
     int32_t skip_insert;
     int32_t freeze_done;         // rollouts: cars of a replica whose agent has arrived no longer move (Env.step returned)
-    int32_t self_clear;          // 1 (sparse ensembles, pipelined kernel only): no whole-table reset - every car resets the
-                                 // entry of the bin it was in one step ago (cell_prev), see pipe_kernel
     int32_t pipe_tma;            // 1: the TMA bulk-copy variant of the pipelined kernel
     int32_t pipe_ctas;           // > 0: launch the software-pipelined persistent kernel with this many car CTAs   // 1: the cell table is built by the sort pipeline (neighbor_sort.cu), not by atomics
     R speed_limit, stop_distance, free_distance, default_acceleration;

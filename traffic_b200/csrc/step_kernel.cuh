@@ -538,6 +538,7 @@ struct OwnRegs {
     __device__ __forceinline__ R rt() const { return rt_; }
     __device__ __forceinline__ int cell() const { return c; }
     __device__ __forceinline__ int sec() const { return sec_; }
+    __device__ __forceinline__ int rep(int r) const { return r; }   // replica of the car (ensembles)
     __device__ __forceinline__ R2 next_curv(int q) const { return a->pt_curv[q]; }
     __device__ __forceinline__ R2 dest(int i) const { return a->dest_xy[i]; }
     __device__ __forceinline__ void after_cross(int, int) {}
@@ -755,7 +756,8 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
                                          int rep, const View<R>& v, R dd_car, int lead, R dd_light, Own& own,
                                          Insert insert) {
     using R2 = typename real2<R>::type;
-    const int cbase = rep * a.g.n_cells, ibase = rep * a.cars_per_replica;
+    // (ensembles: the replica index is asked of the provider where it is needed, not carried across the fp64 sections)
+    auto rep_now = [&]() { return ENS ? own.rep(rep) : 0; };
     const R x = v.x, y = v.y, d_node = v.d_node;
     [[maybe_unused]] const R rt0 = ENS ? own.rt() : R(0);   // start-of-step route time (arrival bookkeeping)
     // ---- velocity law + route advance (simulation.update_cars) ----
@@ -823,7 +825,7 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
         __stcs(&a.d_node[i], d_node);
         __stcs(&a.d_car[i], dd_car != R(0) ? sqrt(dd_car) : R(0));
         __stcs(&a.d_light[i], dd_light != R(0) ? sqrt(dd_light) : dd_light);   // keeps +0 (False) / -0 (None)
-        __stcs(&a.leader[i], lead >= 0 ? lead - ibase : -1);
+        __stcs(&a.leader[i], lead >= 0 ? lead - rep_now() * a.cars_per_replica : -1);
         __stcs(&a.cell_prev[i], c);
     }
     // ---- bin of the new position + insertion into the next step's table ----
@@ -832,15 +834,16 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     const int sec = own.sec();
     if (cn != c) own.store_cell(i, cn);
     // (a car that changed bin has no prefetched entry of its new bin: it simply takes the atomics, ~1 % of the cars)
-    if (!a.skip_insert) insert(cbase + cn, i, cn == c ? sec : TB2_EMPTY);
+    if (!a.skip_insert) insert(rep_now() * a.g.n_cells + cn, i, cn == c ? sec : TB2_EMPTY);
     // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
     // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
-    if (ENS && a.agent_car >= 0 && i - ibase == a.agent_car && !a.done[rep]) {
+    if (ENS && a.agent_car >= 0 && i - rep_now() * a.cars_per_replica == a.agent_car && !a.done[rep_now()]) {
         const R2 d = own.dest(i);
         if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
-            a.done[rep] = 1;
-            a.trip_time[rep] = (double)rt0;
-            a.trip_step[rep] = rot.step_index;
+            const int r = rep_now();
+            a.done[r] = 1;
+            a.trip_time[r] = (double)rt0;
+            a.trip_step[r] = rot.step_index;
             own.on_done();
         }
     }
@@ -975,14 +978,16 @@ struct PipeSmemT {
     R2 ncurv[TB2_PIPE_BLOCK];      // crossing step: curvature constants of the next route point
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
-    int32_t frozen[2][TB2_PIPE_BLOCK];   // ensembles: the car's rollout had already arrived when its tile was requested
-    int32_t cprev[2][TB2_PIPE_BLOCK];    // sparse ensembles (self_clear): the bin the car was in one step ago
+    // ensembles: replica of the car in the slot, -1 if its rollout had already arrived when the tile was requested; replica
+    // of the thread's NEXT tile and that replica's arrival flag (requested one tile ahead, rides in the own-state group)
+    int32_t rep[2][TB2_PIPE_BLOCK], rep_next[TB2_PIPE_BLOCK], done_next[TB2_PIPE_BLOCK];
     // word w of the staged record (w = 2k, 2k+1: table k; 6 + k: go word k)
     __device__ __forceinline__ const int32_t* word(int s, int tid, int w) const {
         return reinterpret_cast<const int32_t*>(&dyn[s][w >> 2][tid]) + (w & 3);
     }
     __device__ __forceinline__ int2 tab_entry(int s, int tid, int k) const { return *reinterpret_cast<const int2*>(word(s, tid, 2 * k)); }
     __device__ __forceinline__ int sec_next(int s, int tid, int k) const { return *word(s, tid, 2 * k + 1); }
+    __device__ __forceinline__ int rep_of(int s, int tid, int) const { return rep[s][tid]; }
     __device__ __forceinline__ uint32_t go_word(int s, int tid, int k) const { return (uint32_t)*word(s, tid, TB2_DYN_GO + k); }
 };
 
@@ -1008,6 +1013,7 @@ struct OwnSmemT {
     __device__ __forceinline__ R rt() const { if constexpr (LATE2) return sm->rt[s][tid]; else return sm->rt[0][tid]; }
     __device__ __forceinline__ int cell() const { return sm->cell[s][tid]; }
     __device__ __forceinline__ int sec() const { return sm->sec_next(s, tid, a->tab_next_k); }
+    __device__ __forceinline__ int rep(int r) const { return sm->rep_of(s, tid, r); }   // re-read where it is used
     __device__ __forceinline__ R2 next_curv(int) const { return sm->ncurv[tid]; }
     __device__ __forceinline__ R2 dest(int i) const { return a->dest_xy[i]; }
     __device__ __forceinline__ void after_cross(int, int) {}
@@ -1044,11 +1050,26 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // flag is sampled once, when the tile's own-state columns are requested, and travels with the staging slot; `done` only
     // ever goes 0 -> 1 and the state of a finished rollout is never looked at again, so a stale 0 merely costs one more
     // (unobserved) step of that replica's cars.
-    auto slot_frozen = [&](int s) { if constexpr (ENS) return sm.frozen[s][tid] != 0; else return false; };
-    auto issue_early = [&](int ii, int s) {
+    // The replica index costs an integer division and the flag a global load: both are produced ONE TILE AHEAD - the
+    // division once per tile, the flag by a cp.async that travels with the previous tile's own-state group - so that
+    // nothing here waits for memory (only the very first tile of a thread asks synchronously).
+    auto slot_frozen = [&](int s) { if constexpr (ENS) return sm.rep[s][tid] < 0; else return false; };
+    auto slot_rep = [&](int s) { if constexpr (ENS) return sm.rep[s][tid]; else return 0; };
+    auto issue_early = [&](int ii, int s, bool first = false) {
         if constexpr (ENS) {
-            const bool fz = ii < a.n_cars && a.freeze_done && a.done[ii / a.cars_per_replica];
-            sm.frozen[s][tid] = fz;
+            bool fz = false;
+            int r = 0;
+            if (ii < a.n_cars) {
+                if (first) { r = ii / a.cars_per_replica; fz = a.freeze_done && a.done[r]; }
+                else { r = sm.rep_next[tid]; fz = a.freeze_done && sm.done_next[tid] != 0; }
+            }
+            sm.rep[s][tid] = fz ? -1 : r;
+            const int nx = ii + stride;   // the thread's next tile: its replica, and (asynchronously) its arrival flag
+            if (nx < a.n_cars) {
+                const int rn = nx / a.cars_per_replica;
+                sm.rep_next[tid] = rn;
+                if (a.freeze_done) cp_async<4>(&sm.done_next[tid], &a.done[rn]);
+            }
             if (fz) { cp_async_commit(); return; }
         }
         if (ii < a.n_cars) {
@@ -1058,7 +1079,6 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
             cp_async<4>(&sm.end[s][tid], &a.path_end[ii]);
             cp_async<4>(&sm.eff[s][tid], &a.path_eff_end[ii]);
             cp_async<4>(&sm.cell[s][tid], &a.cell[ii]);
-            if constexpr (ENS) if (a.self_clear) cp_async<4>(&sm.cprev[s][tid], &a.cell_prev[ii]);
         }
         cp_async_commit();
     };
@@ -1072,7 +1092,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // (shared-memory reads come first in every issue_*: ptxas pads the first LDGSTS after an LDS with three dummy LDS)
     auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
         if (ii < a.n_cars && !slot_frozen(s)) {
-            const int rep = ENS ? ii / a.cars_per_replica : 0;
+            const int rep = slot_rep(s);
             const int cell = sm.cell[s][tid];
             TB2_BOUNDS(cell >= 0 && cell < a.g.n_cells, 4);
             // a car that crosses its path head this step (~1.5 %) steers to the next route point: fetched with the record
@@ -1117,9 +1137,6 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // inside this loop that costs a ten-instruction waterfall per prefetch.)
     auto prefetch_tile_l2 = [&](int first) {
         if ((tid >> 5) != 0 || first + B > a.n_cars) return;
-        if constexpr (ENS) {   // a tile spans at most two rollouts when a rollout has at least B cars
-            if (a.freeze_done && a.done[first / a.cars_per_replica] && a.done[(first + B - 1) / a.cars_per_replica]) return;
-        }
         const int off = (tid & 31) * 128;
         auto pf = [&](const void* base, int bytes) {
             if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + off));
@@ -1145,15 +1162,9 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         for (int k = tid * 16; k < (int)sizeof(sm.logtab); k += B * 16) cp_async<16>(dst + k, src + k);
     }
     griddep_wait();   // everything below reads what the previous step wrote
-    issue_early(i, 0);
+    issue_early(i, 0, true);
     for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
-    // Sparse ensembles (thousands of replicas with more bins than cars each): resetting every bin record of every replica
-    // would move as many sectors as the cars' own state.  Instead every car resets the one entry it can have left in the
-    // table being recycled: that table was filled two steps ago with the bins the cars were in ONE step ago - cell_prev,
-    // kept current by this kernel (written only when it changes) - and the entry shares its sector with the record the car
-    // reads anyway.  (All launches of such a simulation take this path, api.cu:self_clear_mode.)
-    if (!(ENS && a.self_clear))
-        clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
     cp_async_wait<0>();
     __syncthreads();   // every thread's slice of the log table has landed
     issue_dyn(i, 0);
@@ -1172,7 +1183,6 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // a single simulation: a thread past the last car has nothing left to do (there is no block-wide barrier in the
     // loop); an ensemble keeps walking - a later tile may belong to a rollout that is still running
     for (; ENS ? (i - tid < a.n_cars) : (i < a.n_cars); i += stride, s ^= 1) {
-        const int rep = ENS ? i / a.cars_per_replica : 0;
         const bool live = !ENS || (i < a.n_cars && !slot_frozen(s));   // (an arrived rollout is frozen)
         prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
         View<R> v{};                        // pending: G3(k), G1(k+1), GL(k)
@@ -1190,28 +1200,19 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         if (live) {
             const int2 m = sm.tab_entry(s, tid, a.tab_cur_k);
             const int j = (m.x != i) ? m.x : m.y;
-            seg_detect<R>(a, rot.go_cur, rep * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
+            seg_detect<R>(a, rot.go_cur, slot_rep(s) * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
                           sm.go_word(s, tid, a.go_k_cur), own, d_car, lead, d_light);
         }
         cp_async_wait<1>();                 // G1(k+1) landed
         issue_dyn(i + stride, s ^ 1);       // pending: GL(k), G2(k+1)
         cp_async_wait<1>();                 // GL(k) landed
         if (live)
-            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, rep, v, d_car, lead, d_light, own,
+            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, 0, v, d_car, lead, d_light, own,
                                   [&](int rec, int ii, int sec) {
                                       if (ii > sec) return;
                                       pend_old = atomicMin(tab_next + (size_t)(uint32_t)rec * 8u, ii);
                                       pend_rec = rec;
                                   });
-        if constexpr (ENS) {
-            if (a.self_clear && live) {
-                const int co = sm.cprev[s][tid], c = sm.cell[s][tid];
-                TB2_BOUNDS(co >= 0 && co < a.g.n_cells, 8);
-                char* rec = reinterpret_cast<char*>(a.cell_dyn) + ((size_t)(uint32_t)(rep * a.g.n_cells + co) << 5);
-                *reinterpret_cast<int2*>(rec + (uint32_t)a.tab_clear_k * 8u) = make_int2(TB2_EMPTY, TB2_EMPTY);
-                if (co != c) a.cell_prev[i] = c;
-            }
-        }
         cp_async_wait<0>();                 // G2(k+1) landed
         issue_cand_early_late(i + stride, s ^ 1, i + 2 * stride, s);   // pending: G3(k+1), G1(k+2), GL(k+1)
     }
@@ -1272,6 +1273,7 @@ struct PipeTmaSmemT {
     int32_t crossed[TB2_PIPE_BLOCK];
     LogEntry logtab[TB2_LOG_N];
     __device__ __forceinline__ int sec_next(int s, int tid, int) const { return sec[s][tid]; }
+    __device__ __forceinline__ int rep_of(int, int, int r) const { return r; }
 };
 
 template <typename R, bool AUX, bool ENS>
