@@ -187,24 +187,8 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
         tick();
         cl.sync();
     }
-    // The step barrier is split: a thread ARRIVES when its step is written and WAITS only where the next step first looks
-    // at somebody else's data.  The part of a step that needs nothing but the car's own registers - crossed-node test,
-    // target, distance to node, the two linspace axes - runs in between, in the shadow of the slowest warp of the cluster
-    // (barrier skew was a third of the step).  Everything that writes cluster-visible state stays behind the wait.
-    bool pending = false;   // an arrive whose wait is still due
     for (int s = 0; s < pa.n_steps; ++s) {
         const bool do_tick = pa.order != TB2K_ORDER_LIGHTS_CARS || s < pa.n_steps - 1;
-        View<R> v{};
-        if (live) {
-            const bool crossed = view_crossed<R>(a, own.p, own.head, own.cur, own.eff);
-            own.t = crossed ? own.crossing_target_value() : own.head;
-            v = view_build<R>(a, own.p, own.t, own.cur, own.end, own.eff, crossed);
-        }
-        if (pending) {
-            cl.barrier_wait();
-            pending = false;
-            if (ENS && pa.stop_when_done && *s_stop) break;
-        }
         // reset (locally) the table that the step after next will fill
         {
             const int k = (ct + 2) % 3;
@@ -227,6 +211,9 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
                 o = *cl.map_shared_rank(&s_pos[lp * B + (jl % B)], jl / B);
             }
             own.pos_out_slot = &s_pos[(lp ^ 1) * B + tid];
+            const bool crossed = view_crossed<R>(a, own.p, own.head, own.cur, own.eff);
+            own.t = crossed ? own.crossing_target_value() : own.head;
+            const View<R> v = view_build<R>(a, own.p, own.t, own.cur, own.end, own.eff, crossed);
             R d_car, d_light;
             int lead;
             seg_detect<R>(a, rot.go_cur, fbase, own.c, v, j, o, gw, own, d_car, lead, d_light);
@@ -248,10 +235,9 @@ resident_kernel(const __grid_constant__ StepArgsT<R> a, const __grid_constant__ 
         if (do_tick) tick();
         cp ^= 1; lp ^= 1; ct = (ct + 1) % 3;
         ++n_done;
-        cl.barrier_arrive();
-        pending = true;
+        cl.sync();
+        if (ENS && pa.stop_when_done && *s_stop) break;
     }
-    if (pending) cl.barrier_wait();
 
     // ---- write back ----
     const bool complete = n_done == pa.n_steps;
