@@ -179,6 +179,17 @@ int tb2_frame_wait(tb2_sim* sim, int32_t faces_only);
 int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
                     int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit, int32_t max_len,
                     int32_t* path_len, int32_t* path_nodes, void* stream);
+/* tb2_route_paths plus the polylines the initialisers store per car (xpath / ypath): what navigation.shortest_path_lines_nx
+ * + models.path_decompiler build from the node sequence (navigation.py:801-841, models.py:116-137) for a graph whose edges
+ * carry no OSMnx geometry - the positions of the route nodes, a point dropped when it equals its successor, nothing for a
+ * route of fewer than two nodes.  The points are emitted on the device as one compact array: pair p owns
+ * (*path_xy_out)[2*path_ptr[p] ... 2*path_ptr[p+1]) (x, y interleaved; path_ptr has n_pairs + 1 entries).  The point array
+ * belongs to the library (its size is only known after the search): it stays valid until the next tb2_route_polylines /
+ * tb2_route_release call on the same host thread.  node_xy: n_nodes x 2 doubles.  path_nodes may be NULL.  Synchronous. */
+int tb2_route_polylines(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
+                        const double* node_xy, int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit,
+                        int32_t max_len, int32_t* path_len, int32_t* path_nodes, int64_t* path_ptr,
+                        const double** path_xy_out, void* stream);
 const char* tb2_route_last_error(void);
 /* tb2_route_paths keeps its device workspace between calls (per host thread); this frees it */
 void tb2_route_release(void);

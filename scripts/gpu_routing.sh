@@ -17,10 +17,19 @@ for name, nx_, n_pairs, limit in (("c2 64x64, 2000 cars", 64, 2000, None), ("c3 
     else:  # destinations within ~40 hops
         r, c = origin // nx_, origin % nx_
         dest = (np.clip(r + rng.integers(-20, 21, n_pairs), 0, nx_ - 1) * nx_ + np.clip(c + rng.integers(-20, 21, n_pairs), 0, nx_ - 1)).astype(np.int32)
+    routing.shortest_paths(indptr, indices, w, origin[:8], dest[:8], limit=limit, max_len=256)   # context + workspace
     t0 = time.perf_counter()
     pl, pn = routing.shortest_paths(indptr, indices, w, origin, dest, limit=limit, max_len=256)
     el = time.perf_counter() - t0
-    out[name] = {"pairs": n_pairs, "origins": int(n_src), "seconds": el, "routes_per_s": n_pairs / el, "no_path": int((pl < 0).sum()), "mean_len": float(pl[pl > 0].mean())}
+    t0 = time.perf_counter()
+    ptr_h, xy_h = routing.polylines(g.node_xy, pl, pn)                      # host rule (numpy)
+    el_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pl2, pn2, ptr_d, xy_d = routing.route_polylines(indptr, indices, w, g.node_xy, origin, dest, limit=limit, max_len=256)
+    el_dev = time.perf_counter() - t0
+    assert np.array_equal(ptr_h, ptr_d) and np.array_equal(xy_h, xy_d)
+    out[name] = {"pairs": n_pairs, "origins": int(n_src), "seconds": el, "routes_per_s": n_pairs / el, "no_path": int((pl < 0).sum()), "mean_len": float(pl[pl > 0].mean()),
+                 "routes_plus_host_polylines_s": el + el_host, "routes_plus_device_polylines_s": el_dev, "polyline_points": int(ptr_d[-1])}
     print(name, out[name], flush=True)
 json.dump(out, open("gpurun_out/routing_bench.json", "w"), indent=1)
 PY

@@ -44,6 +44,51 @@ def test_gpu_routes_equal_reference_routes(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_dt0.001_p2_s1", "c2_dt0.001_p10_s0"])
+def test_device_polylines_equal_reference_routes(name):
+    """tb2_route_polylines: routes and their polylines in one call, the points emitted on the device as the path-point CSR -
+    identical to the polylines the reference stored for the same cars (and to the host-side rule)."""
+    g = util.load_golden(name)
+    graph = _graph_of(name)
+    key = {tuple(p): i for i, p in enumerate(graph.node_xy)}
+    origin = np.array([key[tuple(p)] for p in g["pos0"]], np.int32)
+    dest = np.array([key[tuple(p)] for p in g["dest_xy"]], np.int32)
+    indptr, indices, w = routing.csr_of(graph.n_nodes, graph.edge_u, graph.edge_v, graph.edge_len)
+    path_len, path_nodes, ptr, xy = routing.route_polylines(indptr, indices, w, graph.node_xy, origin, dest)
+    assert np.array_equal(ptr, g["path_ptr"]) and np.array_equal(xy, g["path_xy"])
+    pl2, pn2 = routing.shortest_paths(indptr, indices, w, origin, dest)
+    assert np.array_equal(path_len, pl2)
+    ptr2, xy2 = routing.polylines(graph.node_xy, pl2, pn2)
+    assert np.array_equal(ptr, ptr2) and np.array_equal(xy, xy2)
+
+
+@pytest.mark.gpu
+def test_device_polylines_drop_duplicate_points_and_handle_degenerate_pairs():
+    """Twin nodes (same position) are dropped as models.path_decompiler drops them (the last of a run survives), a pair
+    with origin == destination or without a path has no points, a too-small point buffer is retried."""
+    graph = synth.SynthGraph(10, 10, seed=4)
+    node_xy = np.array(graph.node_xy, np.float64)
+    u, v, ln = list(graph.edge_u), list(graph.edge_v), list(graph.edge_len)
+    n = graph.n_nodes
+    node_xy = np.vstack([node_xy, node_xy[[5, 17, 40]], [[0.0, 0.0]]])       # three twins + one isolated node
+    for t, a in enumerate((5, 17, 40)):
+        u += [a, n + t]; v += [n + t, a]; ln += [0.0, 0.0]
+        for b in [int(x) for x, y in zip(graph.edge_v, graph.edge_u) if y == a][:2]:
+            u += [n + t, b]; v += [b, n + t]; ln += [float(np.hypot(*(node_xy[a] - node_xy[b]))) * 0.5] * 2   # a shortcut through the twin
+    indptr, indices, w = routing.csr_of(n + 4, u, v, ln)
+    rng = np.random.default_rng(1)
+    origin = np.r_[rng.integers(0, n + 3, 400), [7, 3]].astype(np.int32)
+    dest = np.r_[rng.integers(0, n + 3, 400), [7, n + 3]].astype(np.int32)  # last two: origin == destination, no path
+    path_len, path_nodes, ptr, xy = routing.route_polylines(indptr, indices, w, node_xy, origin, dest)
+    pl2, pn2 = routing.shortest_paths(indptr, indices, w, origin, dest)
+    ptr2, xy2 = routing.polylines(node_xy, pl2, pn2)
+    assert np.array_equal(path_len, pl2) and np.array_equal(ptr, ptr2) and np.array_equal(xy, xy2)
+    assert path_len[-1] == -1 and ptr[-1] == ptr[-2] == ptr[-3]
+    kept = np.diff(ptr)
+    assert (kept < np.maximum(path_len, 0)).any(), "test graph: no duplicate point was ever dropped"
+
+
+@pytest.mark.gpu
 def test_gpu_routes_equal_scipy_on_random_graph():
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import dijkstra

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -147,16 +148,47 @@ __global__ void __launch_bounds__(128) extract_paths_kernel(int n_pairs, int n_n
     path_len[p] = len;
 }
 
+// models.path_decompiler over a node sequence (models.py:116-137) for graphs whose edges carry no geometry: the positions
+// of the route nodes, a point dropped when it equals its successor (the LAST of a run of identical points survives); a
+// route of fewer than two nodes has no edges, hence no points.  One thread per pair; `out` == nullptr only counts.
+__global__ void __launch_bounds__(128) polyline_kernel(int n_pairs, int max_len, const int32_t* __restrict__ path_len,
+                                                       const int32_t* __restrict__ path_nodes,
+                                                       const double2* __restrict__ node_xy,
+                                                       const long long* __restrict__ offset, int32_t* __restrict__ kept_len,
+                                                       double2* __restrict__ out) {
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int len = path_len[p];
+    const int32_t* nodes = path_nodes + (size_t)p * max_len;
+    int kept = 0;
+    if (len >= 2) {
+        double2* dst = out ? out + offset[p] : nullptr;
+        double2 cur = node_xy[nodes[0]];
+        for (int q = 0; q < len; ++q) {
+            const bool last = q == len - 1;
+            double2 nxt = cur;
+            if (!last) nxt = node_xy[nodes[q + 1]];
+            if (last || cur.x != nxt.x || cur.y != nxt.y) {
+                if (dst) dst[kept] = cur;
+                ++kept;
+            }
+            cur = nxt;
+        }
+    }
+    if (!out) kept_len[p] = kept;
+}
+
 thread_local std::string g_route_err;
+thread_local std::vector<double> g_poly;   // polylines of the last tb2_route_polylines call on this thread
 
 // Grow-only device workspace, kept between calls (an initialiser calls tb2_route_paths several times: cars, then one
 // batch per light face set; a dozen cudaMalloc/cudaFree per call cost more than the searches themselves).
 struct RouteWs {
-    void* p[16] = {};
-    size_t cap[16] = {};
+    void* p[20] = {};
+    size_t cap[20] = {};
     int dev = -1;
     void release() {
-        for (int k = 0; k < 16; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
+        for (int k = 0; k < 20; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
     }
 };
 thread_local RouteWs g_ws;
@@ -183,23 +215,27 @@ cudaError_t ws_get(int k, size_t bytes, void** out) {
 extern "C" {
 
 const char* tb2_route_last_error(void) { return g_route_err.c_str(); }
-void tb2_route_release(void) { g_ws.release(); }
+void tb2_route_release(void) { g_ws.release(); std::vector<double>().swap(g_poly); }
 
 // CSR graph on node indices 0..n_nodes-1 (host arrays).  For every pair p writes the node sequence origin..destination
 // to path_nodes[p*max_len ...] and its length to path_len[p] (-1: no path, -2: longer than max_len).  `limit` < 0 means
 // unbounded search; otherwise nodes farther than `limit` from the origin are not explored.  Synchronous.
-int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
-                    int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit, int32_t max_len,
-                    int32_t* path_len, int32_t* path_nodes, void* stream_) {
+static int route_impl(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
+                      const double* node_xy, int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit,
+                      int32_t max_len, int32_t* path_len, int32_t* path_nodes, int64_t* path_ptr, const double** path_xy_out,
+                      void* stream_) {
 #define RCU(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e__ = (call);                                                                   \
         if (e__ != cudaSuccess) { g_route_err = std::string(#call) + ": " + cudaGetErrorString(e__); rc = TB2_ERR_CUDA; goto done; } \
     } while (0)
-    if (n_nodes <= 0 || n_pairs < 0 || max_len <= 0 || !indptr || !indices || !weight) {
-        g_route_err = "tb2_route_paths: bad argument";
+    if (n_nodes <= 0 || n_pairs < 0 || max_len <= 0 || !indptr || !indices || !weight || !path_len ||
+        (!node_xy && !path_nodes) || (node_xy && !(path_ptr && path_xy_out))) {
+        g_route_err = "tb2_route_paths / tb2_route_polylines: bad argument";
         return TB2_ERR_INVALID;
     }
+    if (path_ptr) path_ptr[0] = 0;
+    if (path_xy_out) *path_xy_out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         (void)cudaGetLastError();
@@ -232,7 +268,19 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
     uint8_t* d_flag = nullptr;
     double* d_weight = nullptr;
     unsigned long long* d_dist = nullptr;
-    std::vector<int32_t> sel_pairs, sel_slot, sel_o, sel_d, tmp_len, tmp_nodes;
+    std::vector<int32_t> sel_pairs, sel_slot, sel_o, sel_d, tmp_len, tmp_nodes, tmp_kept;
+    std::vector<int64_t> kept_of_pair(node_xy ? n_pairs : 0, 0);
+    std::vector<long long> tmp_off;
+    std::vector<std::vector<double>> chunk_xy;        // polylines of each chunk, pairs in chunk order
+    std::vector<std::vector<int32_t>> chunk_pairs;
+    double2* d_node_xy = nullptr;
+    double2* d_xy = nullptr;
+    long long* d_off = nullptr;
+    int32_t* d_kept = nullptr;
+    if (node_xy) {
+        RCU(ws_get(13, sizeof(double2) * (size_t)n_nodes, (void**)&d_node_xy));
+        RCU(cudaMemcpyAsync(d_node_xy, node_xy, sizeof(double2) * (size_t)n_nodes, cudaMemcpyDefault, stream));
+    }
     RCU(ws_get(0, sizeof(int32_t) * (n_nodes + 1), (void**)&d_indptr));
     RCU(ws_get(1, sizeof(int32_t) * (n_edges > 0 ? n_edges : 1), (void**)&d_indices));
     RCU(ws_get(2, sizeof(double) * (n_edges > 0 ? n_edges : 1), (void**)&d_weight));
@@ -283,15 +331,55 @@ int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indic
             extract_paths_kernel<<<(np + 127) / 128, 128, 0, stream>>>(np, n_nodes, d_pair_slot, d_origin, d_dest, d_dist, d_pred,
                                                                        max_len, d_len, d_nodes);
             RCU(cudaGetLastError());
-            tmp_len.resize(np); tmp_nodes.resize((size_t)np * max_len);
+            tmp_len.resize(np);
             RCU(cudaMemcpyAsync(tmp_len.data(), d_len, sizeof(int32_t) * np, cudaMemcpyDefault, stream));
-            RCU(cudaMemcpyAsync(tmp_nodes.data(), d_nodes, sizeof(int32_t) * (size_t)np * max_len, cudaMemcpyDefault, stream));
+            if (path_nodes) {
+                tmp_nodes.resize((size_t)np * max_len);
+                RCU(cudaMemcpyAsync(tmp_nodes.data(), d_nodes, sizeof(int32_t) * (size_t)np * max_len, cudaMemcpyDefault, stream));
+            }
+            if (node_xy) {   // polylines of this chunk, emitted on the device as a compact point array
+                RCU(ws_get(14, sizeof(int32_t) * max_pairs, (void**)&d_kept));
+                RCU(ws_get(15, sizeof(long long) * max_pairs, (void**)&d_off));
+                polyline_kernel<<<(np + 127) / 128, 128, 0, stream>>>(np, max_len, d_len, d_nodes, d_node_xy, nullptr, d_kept, nullptr);
+                RCU(cudaGetLastError());
+                tmp_kept.resize(np);
+                RCU(cudaMemcpyAsync(tmp_kept.data(), d_kept, sizeof(int32_t) * np, cudaMemcpyDefault, stream));
+                RCU(cudaStreamSynchronize(stream));
+                tmp_off.resize(np);
+                long long total = 0;
+                for (int k = 0; k < np; ++k) { tmp_off[k] = total; total += tmp_kept[k]; kept_of_pair[pairs[k]] = tmp_kept[k]; }
+                chunk_pairs.push_back(pairs);
+                chunk_xy.emplace_back((size_t)total * 2);
+                if (total > 0) {
+                    RCU(ws_get(16, sizeof(double2) * (size_t)total, (void**)&d_xy));
+                    RCU(cudaMemcpyAsync(d_off, tmp_off.data(), sizeof(long long) * np, cudaMemcpyDefault, stream));
+                    polyline_kernel<<<(np + 127) / 128, 128, 0, stream>>>(np, max_len, d_len, d_nodes, d_node_xy, d_off, nullptr, d_xy);
+                    RCU(cudaGetLastError());
+                    RCU(cudaMemcpyAsync(chunk_xy.back().data(), d_xy, sizeof(double2) * (size_t)total, cudaMemcpyDefault, stream));
+                    RCU(cudaStreamSynchronize(stream));
+                }
+            }
             RCU(cudaStreamSynchronize(stream));
             for (int k = 0; k < np; ++k) {
                 const int p = pairs[k];
                 path_len[p] = tmp_len[k];
+                if (!path_nodes) continue;
                 const int n = tmp_len[k] > 0 ? tmp_len[k] : 0;
                 for (int q = 0; q < n; ++q) path_nodes[(size_t)p * max_len + q] = tmp_nodes[(size_t)k * max_len + q];
+            }
+        }
+    }
+    if (node_xy) {   // CSR over the pairs in the caller's order
+        for (int p = 0; p < n_pairs; ++p) path_ptr[p + 1] = path_ptr[p] + kept_of_pair[p];
+        g_poly.resize((size_t)path_ptr[n_pairs] * 2);
+        double* path_xy = g_poly.data();
+        *path_xy_out = path_xy;
+        for (size_t c = 0; c < chunk_pairs.size(); ++c) {
+            const double* src = chunk_xy[c].data();
+            for (int p : chunk_pairs[c]) {
+                const int64_t n = kept_of_pair[p];
+                if (n > 0) memcpy(path_xy + 2 * path_ptr[p], src, sizeof(double) * 2 * (size_t)n);
+                src += 2 * n;
             }
         }
     }
@@ -299,6 +387,24 @@ done:
     // (device buffers stay in the thread's workspace for the next call; tb2_route_release() frees them)
     return rc;
 #undef RCU
+}
+
+int tb2_route_paths(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
+                    int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit, int32_t max_len,
+                    int32_t* path_len, int32_t* path_nodes, void* stream) {
+    return route_impl(n_nodes, indptr, indices, weight, nullptr, n_pairs, origin, dest, limit, max_len, path_len, path_nodes,
+                      nullptr, nullptr, stream);
+}
+
+// tb2_route_paths + the polylines (xpath / ypath of every pair) as one compact point array, emitted on the device:
+// (*path_xy_out)[2 * path_ptr[p] ... 2 * path_ptr[p + 1]) are the points of pair p.  path_nodes may be NULL.
+int tb2_route_polylines(int32_t n_nodes, const int32_t* indptr, const int32_t* indices, const double* weight,
+                        const double* node_xy, int32_t n_pairs, const int32_t* origin, const int32_t* dest, double limit,
+                        int32_t max_len, int32_t* path_len, int32_t* path_nodes, int64_t* path_ptr,
+                        const double** path_xy_out, void* stream) {
+    if (!node_xy) { g_route_err = "tb2_route_polylines: node_xy is NULL"; return TB2_ERR_INVALID; }
+    return route_impl(n_nodes, indptr, indices, weight, node_xy, n_pairs, origin, dest, limit, max_len, path_len, path_nodes,
+                      path_ptr, path_xy_out, stream);
 }
 
 }  // extern "C"

@@ -57,6 +57,16 @@ def _adjacency_order(graph, ids):
     return [[index[v] for v in graph.G[nid]] for nid in ids.tolist()]
 
 
+def _routes_and_polylines(indptr, indices, w, xy, origins, dests, geom):
+    """Shortest routes and their polylines: one device call for plain graphs (tb2_route_polylines); graphs whose edges
+    carry an OSMnx geometry get their polylines assembled from the edge geometries on the host."""
+    if geom:
+        path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origins, dests)
+        ptr, pxy = routing.polylines_with_geometry(xy, path_len, path_nodes, geom)
+        return path_len, path_nodes, ptr, pxy
+    return routing.route_polylines(indptr, indices, w, xy, origins, dests)
+
+
 def init_random_node_start_location(n, graph, car_id=None, alternate_route=None):
     import pandas as pd
 
@@ -69,9 +79,7 @@ def init_random_node_start_location(n, graph, car_id=None, alternate_route=None)
             origins.append(nodes[i])
             dests.append(nodes[random_index] if random_index != n else nodes[0])
     origins, dests = np.asarray(origins, np.int32), np.asarray(dests, np.int32)
-    path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origins, dests)
-    ptr, pxy = (routing.polylines_with_geometry(xy, path_len, path_nodes, geom) if geom
-                else routing.polylines(xy, path_len, path_nodes))
+    path_len, path_nodes, ptr, pxy = _routes_and_polylines(indptr, indices, w, xy, origins, dests, geom)
     cars_data = []
     for k in range(len(origins)):
         if path_len[k] < 0:                              # NetworkXNoPath: the reference skips the car
@@ -121,9 +129,7 @@ def init_culdesac_start_location(n, graph, car_id=None, alternate_route=None):
                          'Choose a number less than {}'.format(len(culdesacs)))
     origins = np.asarray([culdesacs[i] for i in range(n)], np.int32)
     dests = np.asarray([culdesacs[i + 1] for i in range(n)], np.int32)     # IndexError when n == len(culdesacs), as upstream
-    path_len, path_nodes = routing.shortest_paths(indptr, indices, w, origins, dests)
-    ptr, pxy = (routing.polylines_with_geometry(xy, path_len, path_nodes, geom) if geom
-                else routing.polylines(xy, path_len, path_nodes))
+    path_len, path_nodes, ptr, pxy = _routes_and_polylines(indptr, indices, w, xy, origins, dests, geom)
     cars_data = []
     for k in range(n):
         if path_len[k] < 0:

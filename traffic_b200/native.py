@@ -34,7 +34,8 @@ FIELD_COUNT = 24
 EXPORTS = ["tb2_abi_version", "tb2_last_error", "tb2_arena_bytes", "tb2_create", "tb2_destroy", "tb2_field_info",
            "tb2_field_ptr", "tb2_upload", "tb2_download", "tb2_prepare", "tb2_step", "tb2_step_host", "tb2_cars_update", "tb2_lights_update",
            "tb2_launch_count", "tb2_step_count", "tb2_route_paths", "tb2_route_last_error", "tb2_step_host_async",
-           "tb2_frame_wait", "tb2_rollout", "tb2_download_range", "tb2_debug_bounds_enabled", "tb2_debug_bounds_violations", "tb2_route_release"]
+           "tb2_frame_wait", "tb2_rollout", "tb2_download_range", "tb2_debug_bounds_enabled", "tb2_debug_bounds_violations", "tb2_route_release",
+           "tb2_route_polylines"]
 
 
 class Tb2Config(C.Structure):
@@ -99,6 +100,9 @@ def lib():
         L.tb2_lights_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.tb2_route_paths.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tb2_route_polylines.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.POINTER(C.c_double)), C.c_void_p]
         L.tb2_route_last_error.restype = C.c_char_p
         L.tb2_launch_count.restype = C.c_int64
         L.tb2_launch_count.argtypes = [C.c_void_p]

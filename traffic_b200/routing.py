@@ -3,9 +3,11 @@
 ``shortest_paths`` replaces ``networkx.shortest_path(G, o, d, weight='length')`` for a batch of (origin, destination)
 pairs (``navigation.get_route`` / ``get_init_path`` / ``shortest_path_lines_nx``, ``navigation.py:581-609, 801-841``):
 the reference runs two networkx Dijkstras per car (~16 ms per car, 32 s for 2,000 cars); here one CTA per distinct
-origin runs a label-correcting search on the CSR graph (``csrc/routing.cu``).  ``polylines`` turns node sequences into
-the ``xpath`` / ``ypath`` polylines of ``models.path_decompiler`` (``models.py:116-137``) for graphs whose edges carry no
-``geometry``: the node positions origin..destination with consecutive duplicates dropped.
+origin runs a label-correcting search on the CSR graph (``csrc/routing.cu``).  ``route_polylines`` also emits, on the
+device, the ``xpath`` / ``ypath`` polylines of ``models.path_decompiler`` (``models.py:116-137``) for graphs whose edges
+carry no ``geometry`` - the node positions origin..destination with consecutive duplicates dropped - as the compact
+path-point CSR the step kernels consume; ``polylines`` is the same rule on the host (numpy), kept as its cross-check and for
+node sequences that did not come from the router.
 """
 from __future__ import annotations
 
@@ -53,6 +55,44 @@ def shortest_paths(indptr, indices, weights, origin, dest, limit: float | None =
             raise native.NativeError("tb2_route_paths: predecessor walk exceeded the number of nodes (%d pairs)"
                                      % int((path_len == -2).sum()))
         return path_len, path_nodes
+
+
+def route_polylines(indptr, indices, weights, node_xy, origin, dest, limit: float | None = None, max_len: int | None = None):
+    """``shortest_paths`` + ``polylines`` in one call, the polylines emitted on the device as the path-point CSR the step
+    kernels consume (``tb2_route_polylines``).  Returns ``(path_len, path_nodes, path_ptr[int64 n+1], path_xy[float64 P,2])``."""
+    L = native.lib()
+    indptr = np.ascontiguousarray(indptr, np.int32)
+    indices = np.ascontiguousarray(indices, np.int32)
+    weights = np.ascontiguousarray(weights, np.float64)
+    node_xy = np.ascontiguousarray(node_xy, np.float64).reshape(-1, 2)
+    origin = np.ascontiguousarray(origin, np.int32)
+    dest = np.ascontiguousarray(dest, np.int32)
+    n_nodes, n_pairs = len(indptr) - 1, len(origin)
+    if len(node_xy) != n_nodes:
+        raise ValueError("node_xy must hold one position per node")
+    if max_len is None:
+        max_len = n_nodes
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    while True:
+        path_len = np.empty(n_pairs, np.int32)
+        path_nodes = np.empty((n_pairs, max_len), np.int32)
+        path_ptr = np.zeros(n_pairs + 1, np.int64)
+        xy_ptr = C.POINTER(C.c_double)()
+        rc = L.tb2_route_polylines(n_nodes, p(indptr), p(indices), p(weights), p(node_xy), n_pairs, p(origin), p(dest),
+                                   C.c_double(-1.0 if limit is None else float(limit)), max_len, p(path_len), p(path_nodes),
+                                   p(path_ptr), C.byref(xy_ptr), None)
+        if rc != 0:
+            raise native.NativeError("tb2_route_polylines failed (status %d): %s" % (rc, L.tb2_route_last_error().decode()))
+        if n_pairs and (path_len == -2).any():
+            if max_len < n_nodes:
+                max_len = min(n_nodes, max_len * 4)   # a path did not fit: retry with a longer buffer
+                continue
+            raise native.NativeError("tb2_route_polylines: predecessor walk exceeded the number of nodes (%d pairs)"
+                                     % int((path_len == -2).sum()))
+        total = int(path_ptr[-1])
+        # the point array belongs to the library until the next routing call: copy it out
+        path_xy = (np.ctypeslib.as_array(xy_ptr, shape=(total, 2)).copy() if total else np.zeros((0, 2), np.float64))
+        return path_len, path_nodes, path_ptr, path_xy
 
 
 def polylines(node_xy, path_len, path_nodes):
