@@ -468,11 +468,13 @@ __device__ __forceinline__ void lights_tick_body(int lg, int n_lights_total, int
                                                  int n_cells, double dt, const double* __restrict__ switch_time,
                                                  const int32_t* __restrict__ face_ptr, const uint8_t* __restrict__ go_cur,
                                                  uint8_t* __restrict__ go_next, const double* t_cur, double* t_next,
-                                                 const int2* __restrict__ light_cellinfo, CellDynT* cell_dyn, int go_k_next) {
+                                                 const int2* __restrict__ light_cellinfo, CellDynT* cell_dyn, int go_k_next,
+                                                 const int32_t* __restrict__ frozen = nullptr) {
     const double t = __dadd_rn(*t_cur, dt);
     if (lg == 0) *t_next = t;
     if (lg >= n_lights_total) return;
     const int rep = lg / lights_per_replica, l = lg - rep * lights_per_replica;
+    if (frozen && frozen[rep]) return;   // rollouts: nobody looks at the lights of a replica whose agent has arrived
     const int fbase = rep * faces_per_replica;
     const double sw = switch_time[lg];
     double r = fmod(t, sw);                       // numpy float remainder
@@ -910,7 +912,8 @@ __global__ void __launch_bounds__(TB2_BLOCK, TB2_MIN_BLOCKS) step_kernel(const _
     if ((int)blockIdx.x >= a.car_blocks) {
         const int l = ((int)blockIdx.x - a.car_blocks) * TB2_BLOCK + (int)threadIdx.x;
         lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
-                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
+                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1,
+                         (ENS && a.freeze_done) ? a.done : nullptr);
         return;
     }
     const LogEntry* logtab = reinterpret_cast<const LogEntry*>(a.log_table);   // 4 KB, L1-resident
@@ -1040,7 +1043,8 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         const int l = ((int)blockIdx.x - a.pipe_ctas) * B + tid;
         griddep_wait();
         lights_tick_body(l, a.n_lights, a.lights_per_replica, a.faces_per_replica, a.g.n_cells, a.dt64, a.switch_time,
-                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1);
+                         a.face_ptr, a.go_cur, a.go_next, a.t_cur, a.t_next, a.light_cellinfo, a.cell_dyn, a.go_k_cur ^ 1,
+                         (ENS && a.freeze_done) ? a.done : nullptr);
         return;
     }
     const int stride = a.pipe_ctas * B;
@@ -1164,7 +1168,18 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     griddep_wait();   // everything below reads what the previous step wrote
     issue_early(i, 0, true);
     for (int q = 1; q < TB2_PIPE_L2_AHEAD; ++q) prefetch_tile_l2((int)blockIdx.x * B + q * stride);
-    clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    if (ENS && a.freeze_done) {
+        // rollouts: the tables of a replica whose agent has arrived are dead - whole replicas are skipped (late in a sweep
+        // most of them are), a CTA resets the records of every pipe_ctas-th replica
+        for (int rp = (int)blockIdx.x; rp < a.n_replicas; rp += a.pipe_ctas) {
+            if (a.done[rp]) continue;
+            CellDynT* dyn = a.cell_dyn + (size_t)rp * a.g.n_cells;
+            for (int r = tid; r < a.g.n_cells; r += B)
+                *reinterpret_cast<int2*>(&dyn[r].w[2 * a.tab_clear_k]) = make_int2(TB2_EMPTY, TB2_EMPTY);
+        }
+    } else {
+        clear_table(a.cell_dyn, a.tab_clear_k, a.g.n_cells * a.n_replicas, (int)blockIdx.x * B + tid, stride);
+    }
     cp_async_wait<0>();
     __syncthreads();   // every thread's slice of the log table has landed
     issue_dyn(i, 0);
