@@ -951,10 +951,6 @@ __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem)), "l"(gmem), "n"(BYTES) : "memory");
 }
-// cp.async.bulk.prefetch.L2: one instruction pulls `bytes` contiguous bytes (16-byte granular) from HBM into L2
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, int bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
