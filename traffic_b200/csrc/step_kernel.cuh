@@ -761,7 +761,19 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     // (ensembles: the replica index is asked of the provider where it is needed, not carried across the fp64 sections)
     auto rep_now = [&]() { return ENS ? own.rep(rep) : 0; };
     const R x = v.x, y = v.y, d_node = v.d_node;
-    [[maybe_unused]] const R rt0 = ENS ? own.rt() : R(0);   // start-of-step route time (arrival bookkeeping)
+    // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
+    // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5); it needs nothing but the
+    // start-of-step state, so it runs first - nothing of it stays live across the arithmetic below
+    if (ENS && a.agent_car >= 0 && i - rep_now() * a.cars_per_replica == a.agent_car && !a.done[rep_now()]) {
+        const R2 d = own.dest(i);
+        if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
+            const int r = rep_now();
+            a.done[r] = 1;
+            a.trip_time[r] = (double)own.rt();   // start-of-step route time
+            a.trip_step[r] = rot.step_index;
+            own.on_done();
+        }
+    }
     // ---- velocity law + route advance (simulation.update_cars) ----
     R vx = R(0), vy = R(0);
     if (v.has_path) {
@@ -837,18 +849,6 @@ __device__ __forceinline__ void seg_move(const StepArgsT<R>& a, const Rot<R>& ro
     if (cn != c) own.store_cell(i, cn);
     // (a car that changed bin has no prefetched entry of its new bin: it simply takes the atomics, ~1 % of the cars)
     if (!a.skip_insert) insert(rep_now() * a.g.n_cells + cn, i, cn == c ? sec : TB2_EMPTY);
-    // rollout bookkeeping: Env.simulation_step tests FrontView.end_of_route on the agent BEFORE stepping
-    // (environment.py:161-171, navigation.py:113-128; FrontView's default stop_distance is 5)
-    if (ENS && a.agent_car >= 0 && i - rep_now() * a.cars_per_replica == a.agent_car && !a.done[rep_now()]) {
-        const R2 d = own.dest(i);
-        if (isclose_<R>(R(0), d.x - x, R(1.0e-5), R(5.0)) && isclose_<R>(R(0), d.y - y, R(1.0e-5), R(5.0))) {
-            const int r = rep_now();
-            a.done[r] = 1;
-            a.trip_time[r] = (double)rt0;
-            a.trip_step[r] = rot.step_index;
-            own.on_done();
-        }
-    }
 }
 
 // Dependent-load waves of the plain (non-pipelined) form: (1) own state, coalesced; (2) the bin's dynamic record - table
