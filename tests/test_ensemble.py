@@ -130,6 +130,61 @@ def test_ensemble_matches_one_oracle_run_per_replica(R, chunk):
 
 
 @pytest.mark.gpu
+def test_large_ensemble_takes_the_pipelined_kernel_and_matches_the_oracle():
+    """An ensemble big enough (160 x 1,500 = 240k cars) to take the software-pipelined kernel on its own - the path of
+    BASELINE configs[4] - with frozen rollouts: a sample of replicas is compared with one oracle run each (arrival step and
+    trip time; full state for the replicas that never arrive, which are stepped to the end)."""
+    from oracle import oracle
+    from traffic_b200 import native, synth
+
+    w0, _ = synth.make_city(nx_=32, ny_=32, n_cars=1500, prescale=3, seed=21, max_hops=6)
+    dt, steps, R = 1e-3, 600, 160
+    lens = w0.path_end - w0.path_start
+    agent = int(np.flatnonzero((lens >= 1) & (lens <= 2))[0])
+    ens = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
+    l0 = ens.sim.launch_count
+    res = ens.rollout(dt, steps)
+    # the batched form: one launch per step, the done flags read back every 256 steps (it may stop at such a boundary)
+    assert ens.sim.launch_count - l0 >= 256, "expected one launch per step (the batched form)"
+    assert 0 < res[:, 2].sum(), "test world: no agent arrived"
+    sample = list(range(0, R, 23)) + [R - 1]
+    checked_state = 0
+    for r in sample:
+        wc = w0.copy()
+        wc.switch_time = ens.switch_time[r].copy()
+        trip = None
+        for k in range(steps):
+            d = wc.dest_xy[agent] - wc.pos[agent]
+            if np.isclose(0, d[0], atol=5) and np.isclose(0, d[1], atol=5):   # environment.py:161-171: tested before stepping
+                trip = (wc.route_time[agent], k)
+                break
+            oracle.run(wc, dt, 1, oracle.ORDER_LIGHTS_CARS)
+        if trip is None:
+            assert res[r, 2] == 0 and res[r, 1] == steps and ens.sim.step_count == steps
+            wg = ens.sim.download_world(w0.copy(), replica=r)
+            for f in ("cursor", "cell", "leader", "face_go"):
+                assert np.array_equal(getattr(wg, f), getattr(wc, f)), "replica %d field %s" % (r, f)
+            assert np.allclose(wg.pos, wc.pos, rtol=1e-12, atol=0)
+            checked_state += 1
+        else:
+            assert res[r, 2] == 1 and res[r, 1] == trip[1] and abs(res[r, 0] - trip[0]) < 1e-12, (r, res[r], trip)
+    # full state of a few replicas after a fixed number of steps on the same path (no rollout, nobody frozen)
+    ens2 = ensemble.Ensemble(w0, replica_ids=np.arange(R), agent_car=agent, seed=5, write_aux=True)
+    ens2.sim.step(dt, 61, oracle.ORDER_LIGHTS_CARS)
+    for r in (0, 77, R - 1):
+        wc = w0.copy()
+        wc.switch_time = ens2.switch_time[r].copy()
+        oracle.run(wc, dt, 61, oracle.ORDER_LIGHTS_CARS)
+        wg = ens2.sim.download_world(w0.copy(), replica=r)
+        for f in ("cursor", "cell", "leader", "face_go"):
+            assert np.array_equal(getattr(wg, f), getattr(wc, f)), "replica %d field %s" % (r, f)
+        assert np.allclose(wg.pos, wc.pos, rtol=1e-12, atol=0)
+        checked_state += 1
+    print("large ensemble: %d of %d sampled rollouts arrived, %d replicas compared state for state" %
+          (len(sample), len(sample), checked_state))
+
+
+@pytest.mark.gpu
 def test_rollout_launch_stops_each_replica_at_arrival():
     """tb2_rollout: one launch, every replica (one thread-block cluster, world on chip) leaves when its agent has arrived;
     trip time / steps / done must equal what the fixed-length batched run records, and an arrived replica stays frozen."""
