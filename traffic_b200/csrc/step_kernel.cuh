@@ -46,7 +46,7 @@
 #define TB2_PIPE_BLOCK 128         // threads per CTA of the pipelined big-world kernel (cars per tile)
 #endif
 #ifndef TB2_PIPE_MIN_BLOCKS
-#define TB2_PIPE_MIN_BLOCKS 5      // resident CTAs per SM (96 registers per thread, no spills; ~36 KB of staging per CTA)
+#define TB2_PIPE_MIN_BLOCKS 5      // resident CTAs per SM (96 registers per thread, one 4-byte spill; ~42 KB of staging per CTA)
 #endif
 #ifndef TB2_PIPE_L2_AHEAD
 #define TB2_PIPE_L2_AHEAD 3        // own-state columns are bulk-prefetched into L2 this many tiles ahead
