@@ -42,7 +42,7 @@ enum Buf {
     B_D_NODE, B_D_CAR, B_D_LIGHT, B_CELL, B_CELL_PREV, B_LEADER, B_CELL_DYN, B_LIGHT_XY, B_SWITCH_TIME, B_FACE_PTR,
     B_FACE_VEC, B_GO0, B_GO1, B_CELL_LIGHT_PTR, B_CELL_LIGHT_IDX, B_T0, B_T1, B_HEAD_XY, B_HEAD_CURV, B_PT_CURV,
     B_FACE_UNIT, B_DONE, B_TRIP_TIME, B_TRIP_STEP, B_CELL_STAT, B_LIGHT_CELLINFO, B_LOG_TABLE, B_FRAME_STAGE, B_GO_STAGE, B_SORT_KEYS_IN, B_SORT_VALS_IN, B_SORT_KEYS_OUT,
-    B_SORT_VALS_OUT, B_SORT_TEMP, B_COUNT
+    B_SORT_VALS_OUT, B_SORT_TEMP, B_LIVE_LIST, B_DONE_V, B_COUNT
 };
 
 struct Layout {
@@ -105,7 +105,7 @@ Layout make_layout(const tb2_config& c) {
     b[B_CELL_LIGHT_PTR] = (C + 1) * 4;
     b[B_CELL_LIGHT_IDX] = LC * 4;
     b[B_T0] = b[B_T1] = 8;
-    b[B_DONE] = b[B_TRIP_STEP] = Rep * 4;
+    b[B_DONE] = b[B_TRIP_STEP] = b[B_LIVE_LIST] = b[B_DONE_V] = Rep * 4;
     b[B_TRIP_TIME] = Rep * 8;
     b[B_CELL_STAT] = C * 32;
     b[B_LIGHT_CELLINFO] = L * 8;
@@ -136,6 +136,7 @@ struct tb2_sim {
     int cur_pos = 0, cur_tab = 0, cur_go = 0, cur_t = 0;
     bool prepared = false;
     bool freeze_done = false;       // inside tb2_rollout: arrived replicas are frozen
+    int n_live = 0;                 // inside tb2_rollout, > 0: B_LIVE_LIST holds the replicas still running (walked by pipe_kernel)
     bool go_dirty = false;          // TB2_FACE_GO was uploaded: the per-bin go words must be re-derived before the next step
     bool allow_pipe = true;         // TB2_NO_PIPE=1: big worlds use the plain one-thread-per-car kernel (A/B testing)
     bool pipe_tma = false;          // TB2_PIPE_TMA=1: own-state columns travel as TMA bulk copies (measured slower, see step_kernel.cuh)
@@ -299,6 +300,12 @@ void step_cars_t(tb2_sim* s, double dt, int tick, int aux, cudaStream_t stream) 
     }
     a.skip_insert = s->cfg.neighbor_mode == TB2_NEIGHBOR_SORT;
     a.freeze_done = s->freeze_done ? 1 : 0;
+    // the live-replica list only means something to the pipelined ensemble kernel; every other form walks all replicas
+    const bool walk_live = s->n_live > 0 && s->freeze_done && a.pipe_ctas > 0 && !a.pipe_tma;
+    a.live_list = walk_live ? s->buf<int32_t>(B_LIVE_LIST) : nullptr;
+    a.done_v = s->buf<int32_t>(B_DONE_V);
+    a.n_live = walk_live ? s->n_live : 0;
+    a.n_walk = walk_live ? s->n_live * s->cfg.n_cars : a.n_cars;
     launch_step(a, stream);
     if (a.skip_insert)   // north_star's pipeline: radix sort by bin + segment heads -> the same table
         s->launches += neighbor_sort_build(a.n_cars, a.cars_per_replica, s->n_cells, key_bits_of(s->cfg), a.cell,
@@ -605,9 +612,11 @@ int tb2_rollout(tb2_sim* s, double dt, int32_t max_steps, int32_t order, void* s
         // large ensembles: batched launches; the cars of an arrived replica stop moving, and every `chunk` steps the done
         // flags (4 bytes per replica) are read back to leave as soon as every rollout is over
         const int R = s->cfg.n_replicas, chunk = 256;
-        int32_t* done_h = nullptr;
-        CU(cudaMallocHost(reinterpret_cast<void**>(&done_h), sizeof(int32_t) * (size_t)R));
+        int32_t* done_h = nullptr;   // [0, R): done flags read back; [R, 2R): the live-replica list on its way to the device
+        CU(cudaMallocHost(reinterpret_cast<void**>(&done_h), sizeof(int32_t) * 2 * (size_t)R));
+        int32_t* live_h = done_h + R;
         s->freeze_done = true;
+        s->n_live = 0;
         int rc = TB2_OK;
         const bool was_persistent = s->allow_persistent;
         s->allow_persistent = false;   // per-step launches (the cooperative kernel has no frozen-replica path)
@@ -618,12 +627,21 @@ int tb2_rollout(tb2_sim* s, double dt, int32_t max_steps, int32_t order, void* s
             if (rc != TB2_OK) break;
             if (cudaMemcpyAsync(done_h, s->buf<int32_t>(B_DONE), sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
                 cudaStreamSynchronize(stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "tb2_rollout readback"); break; }
-            bool all = true;
-            for (int r = 0; r < R && all; ++r) all = done_h[r] != 0;
-            if (all) break;
+            // the replicas still running: from now on the pipelined kernel walks only their cars (a replica that arrives
+            // before the next read-back is frozen through its done_v flag)
+            int n_live = 0;
+            for (int r = 0; r < R; ++r) if (done_h[r] == 0) live_h[n_live++] = r;
+            if (n_live == 0) break;
+            if (n_live < R) {
+                if (cudaMemcpyAsync(s->buf<int32_t>(B_LIVE_LIST), live_h, sizeof(int32_t) * (size_t)n_live, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+                    cudaMemsetAsync(s->buf<int32_t>(B_DONE_V), 0, sizeof(int32_t) * (size_t)n_live, stream) != cudaSuccess ||
+                    cudaStreamSynchronize(stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "tb2_rollout live list"); break; }
+                s->n_live = n_live;
+            }
         }
         s->allow_persistent = was_persistent;
         s->freeze_done = false;
+        s->n_live = 0;
         cudaFreeHost(done_h);
         return rc;
     }

@@ -113,6 +113,12 @@ struct StepArgsT {
     double* t_next;
     // replica-ensemble bookkeeping (environment.py:120-126, 154-173)
     int32_t* done;
+    // long sweeps (tb2_rollout, pipelined kernel): the replicas that were still running at the last read-back; the kernel
+    // walks only their cars.  done_v: arrival flags indexed like live_list.  nullptr / 0: every replica is walked
+    const int32_t* live_list;
+    int32_t* done_v;
+    int32_t n_live;
+    int32_t n_walk;   // car positions the pipelined kernel walks: n_live * cars_per_replica with a list, else n_cars
     double* trip_time;
     int32_t* trip_step;
 };

@@ -980,6 +980,10 @@ struct PipeSmemT {
     // ensembles: replica of the car in the slot, -1 if its rollout had already arrived when the tile was requested; replica
     // of the thread's NEXT tile and that replica's arrival flag (requested one tile ahead, rides in the own-state group)
     int32_t rep[2][TB2_PIPE_BLOCK], rep_next[TB2_PIPE_BLOCK], done_next[TB2_PIPE_BLOCK];
+    // ensembles: global index of the car in the slot (-1: none) - with a live-replica list the loop walks the cars of the
+    // replicas still running, not all of them - and the car's index within its replica for the thread's next tile
+    int32_t idx[2][TB2_PIPE_BLOCK], c_next[TB2_PIPE_BLOCK];
+    int32_t pend_car[TB2_PIPE_BLOCK];   // ensembles: the car whose table insertion is half done (walk positions are not cars)
     // word w of the staged record (w = 2k, 2k+1: table k; 6 + k: go word k)
     __device__ __forceinline__ const int32_t* word(int s, int tid, int w) const {
         return reinterpret_cast<const int32_t*>(&dyn[s][w >> 2][tid]) + (w & 3);
@@ -999,13 +1003,15 @@ struct OwnSmemT {
     bool crossed;
     const StepArgsT<R>* a;
     R2* pos_out;
+    int vv = 0;   // position of the car in the walk over the live replicas (ensembles with a live-replica list)
     __device__ __forceinline__ void store_route_time(int i, R v) { a->route_time[i] = v; }
     __device__ __forceinline__ void store_cursor(int i, int v) { a->cursor[i] = v; }
     __device__ __forceinline__ void store_head(int i, R2 v) { a->head_xy[i] = v; }
     __device__ __forceinline__ void store_head_curv(int i, R2 v) { a->head_curv[i] = v; }
     __device__ __forceinline__ void store_pos(int i, R2 v) { pos_out[i] = v; }
     __device__ __forceinline__ void store_cell(int i, int v) { a->cell[i] = v; }
-    __device__ __forceinline__ void on_done() {}
+    // the agent has arrived: also raise the flag the walk over the live-replica list looks at
+    __device__ __forceinline__ void on_done() { if (a->live_list) a->done_v[vv / a->cars_per_replica] = 1; }
     __device__ __forceinline__ R2 target() const { return crossed ? sm->tgt[s][tid] : sm->head[s][tid]; }
     __device__ __forceinline__ int3 route() const { return make_int3(sm->cur[s][tid], sm->end[s][tid], sm->eff[s][tid]); }
     __device__ __forceinline__ R2 hc() const { if constexpr (LATE2) return sm->hc[s][tid]; else return sm->hc[0][tid]; }
@@ -1055,24 +1061,50 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // nothing here waits for memory (only the very first tile of a thread asks synchronously).
     auto slot_frozen = [&](int s) { if constexpr (ENS) return sm.rep[s][tid] < 0; else return false; };
     auto slot_rep = [&](int s) { if constexpr (ENS) return sm.rep[s][tid]; else return 0; };
-    auto issue_early = [&](int ii, int s, bool first = false) {
+    // Long sweeps: tb2_rollout hands the kernel the list of the replicas that were still running at its last read-back
+    // (live_list, n_live); the loop then walks n_live * cars_per_replica "virtual" car indices - position k of the list
+    // times cars_per_replica plus the car's index in its replica - instead of every car of every replica.  The list entry
+    // and the arrival flag (done_v, indexed like the list) of the next tile are both fetched one tile ahead.  Everything
+    // after issue_early takes the car's global index from the staging slot.
+#define n_walk (a.n_walk)   /* = n_live * cars_per_replica, or n_cars without a list: read from the constant bank */
+    auto car_of = [&](int vv, int s) {   // global car index of walk position vv staged in slot s, -1 if there is none
+        if constexpr (ENS) return sm.idx[s][tid]; else return vv < a.n_cars ? vv : -1;
+    };
+    auto issue_early = [&](int vv, int s, bool first = false) {
+        int ii = vv < a.n_cars ? vv : -1;
         if constexpr (ENS) {
             bool fz = false;
             int r = 0;
-            if (ii < a.n_cars) {
-                if (first) { r = ii / a.cars_per_replica; fz = a.freeze_done && a.done[r]; }
-                else { r = sm.rep_next[tid]; fz = a.freeze_done && sm.done_next[tid] != 0; }
+            ii = -1;
+            if (vv < n_walk) {
+                int c;
+                if (first) {
+                    const int rv = vv / a.cars_per_replica;
+                    c = vv - rv * a.cars_per_replica;
+                    r = a.live_list ? a.live_list[rv] : rv;
+                    fz = a.freeze_done && (a.live_list ? a.done_v[rv] : a.done[r]);
+                } else {
+                    r = sm.rep_next[tid]; c = sm.c_next[tid]; fz = a.freeze_done && sm.done_next[tid] != 0;
+                }
+                ii = r * a.cars_per_replica + c;
             }
             sm.rep[s][tid] = fz ? -1 : r;
-            const int nx = ii + stride;   // the thread's next tile: its replica, and (asynchronously) its arrival flag
-            if (nx < a.n_cars) {
+            sm.idx[s][tid] = ii;
+            const int nx = vv + stride;   // the thread's next tile: its replica, and (asynchronously) its arrival flag
+            if (nx < n_walk) {
                 const int rn = nx / a.cars_per_replica;
-                sm.rep_next[tid] = rn;
-                if (a.freeze_done) cp_async<4>(&sm.done_next[tid], &a.done[rn]);
+                sm.c_next[tid] = nx - rn * a.cars_per_replica;
+                if (a.live_list) {
+                    cp_async<4>(&sm.rep_next[tid], &a.live_list[rn]);
+                    if (a.freeze_done) cp_async<4>(&sm.done_next[tid], &a.done_v[rn]);
+                } else {
+                    sm.rep_next[tid] = rn;
+                    if (a.freeze_done) cp_async<4>(&sm.done_next[tid], &a.done[rn]);
+                }
             }
             if (fz) { cp_async_commit(); return; }
         }
-        if (ii < a.n_cars) {
+        if (ii >= 0) {
             cp_async<sizeof(R2)>(&sm.pos[s][tid], &a.pos_in[ii]);
             cp_async<sizeof(R2)>(&sm.head[s][tid], &a.head_xy[ii]);
             cp_async<4>(&sm.cur[s][tid], &a.cursor[ii]);
@@ -1082,16 +1114,18 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         }
         cp_async_commit();
     };
-    auto issue_late = [&](int ii, int s) {
-        if (ii < a.n_cars && !slot_frozen(s)) {
+    auto issue_late = [&](int vv, int s) {
+        const int ii = car_of(vv, s);
+        if (ii >= 0 && !slot_frozen(s)) {
             cp_async<sizeof(R2)>(&sm.hc[0][tid], &a.head_curv[ii]);
             cp_async<sizeof(R)>(&sm.rt[0][tid], &a.route_time[ii]);
         }
         cp_async_commit();
     };
     // (shared-memory reads come first in every issue_*: ptxas pads the first LDGSTS after an LDS with three dummy LDS)
-    auto issue_dyn = [&](int ii, int s) {     // needs G1 of that tile
-        if (ii < a.n_cars && !slot_frozen(s)) {
+    auto issue_dyn = [&](int vv, int s) {     // needs G1 of that tile
+        const int ii = car_of(vv, s);
+        if (ii >= 0 && !slot_frozen(s)) {
             const int rep = slot_rep(s);
             const int cell = sm.cell[s][tid];
             TB2_BOUNDS(cell >= 0 && cell < a.g.n_cells, 4);
@@ -1108,10 +1142,11 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         cp_async_commit();
     };
     // G3 of tile `ii` (needs its G2), G1 of tile `i2` and GL of tile `ii`, committed in the order the loop consumes them
-    auto issue_cand_early_late = [&](int ii, int s, int i2, int s2) {
+    auto issue_cand_early_late = [&](int vv, int s, int i2, int s2) {
         int j = TB2_EMPTY, cell = 0, cur = 0, end = 0;
         bool has_light = false, crossed = false;
-        if (ii < a.n_cars && !slot_frozen(s)) {
+        const int ii = car_of(vv, s);
+        if (ii >= 0 && !slot_frozen(s)) {
             const int2 m = sm.tab_entry(s, tid, a.tab_cur_k);
             j = (m.x != ii) ? m.x : m.y;
             TB2_BOUNDS(j == TB2_EMPTY || (j >= 0 && j < a.n_cars && j != ii), 5);
@@ -1128,7 +1163,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         if (crossed && cur + 1 < end) cp_async<sizeof(R2)>(&sm.ncurv[tid], &a.pt_curv[cur + 1]);
         cp_async_commit();
         issue_early(i2, s2);
-        issue_late(ii, s);
+        issue_late(vv, s);
     };
 
     // Warp 0 of each CTA pulls the own-state columns of the tile TB2_PIPE_L2_AHEAD iterations ahead from HBM into L2 (whole
@@ -1137,6 +1172,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     // inside this loop that costs a ten-instruction waterfall per prefetch.)
     auto prefetch_tile_l2 = [&](int first) {
         if ((tid >> 5) != 0 || first + B > a.n_cars) return;
+        if (ENS && a.live_list) return;   // (walk positions are not addresses; the tile is requested two tiles ahead anyway)
         const int off = (tid & 31) * 128;
         auto pf = [&](const void* base, int bytes) {
             if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + off));
@@ -1186,20 +1222,23 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
     int32_t* const tab_next = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a.cell_dyn) + (uint32_t)a.tab_next_k * 8u);
     auto finish_insert = [&](int ii) {
         if (pend_rec < 0) return;
+        if constexpr (ENS) ii = sm.pend_car[tid];
         const int loser = pend_old > ii ? pend_old : ii;   // whoever is not the bin minimum competes for second place
         if (loser != TB2_EMPTY) atomicMin(tab_next + (size_t)(uint32_t)pend_rec * 8u + 1, loser);
         pend_rec = -1;
     };
     int s = 0;
     // a single simulation: a thread past the last car has nothing left to do (there is no block-wide barrier in the
-    // loop); an ensemble keeps walking - a later tile may belong to a rollout that is still running
-    for (; ENS ? (i - tid < a.n_cars) : (i < a.n_cars); i += stride, s ^= 1) {
-        const bool live = !ENS || (i < a.n_cars && !slot_frozen(s));   // (an arrived rollout is frozen)
+    // loop); an ensemble keeps walking - a later tile may belong to a rollout that is still running.  `i` is the position
+    // in the walk, `ic` the car (the same thing unless a live-replica list is in use)
+    for (; ENS ? (i - tid < n_walk) : (i < a.n_cars); i += stride, s ^= 1) {
+        const int ic = ENS ? car_of(i, s) : i;
+        const bool live = !ENS || (ic >= 0 && !slot_frozen(s));   // (an arrived rollout is frozen)
         prefetch_tile_l2(i - tid + TB2_PIPE_L2_AHEAD * stride);
         View<R> v{};                        // pending: G3(k), G1(k+1), GL(k)
         // the staged operands stay in shared memory; whoever needs one of them re-reads it (LDS) where it is used
         // instead of keeping it in a register across the fp64 sections
-        OwnSmemT<R, PipeSmemT<R>, false> own{&sm, s, tid, false, &a, rot.pos_out};
+        OwnSmemT<R, PipeSmemT<R>, false> own{&sm, s, tid, false, &a, rot.pos_out, i};
         if (live) {
             own.crossed = sm.crossed[tid] != 0;
             v = view_build<R>(a, sm.pos[s][tid], own.target(), sm.cur[s][tid], sm.end[s][tid], sm.eff[s][tid], own.crossed);
@@ -1210,7 +1249,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         int lead = -1;
         if (live) {
             const int2 m = sm.tab_entry(s, tid, a.tab_cur_k);
-            const int j = (m.x != i) ? m.x : m.y;
+            const int j = (m.x != ic) ? m.x : m.y;
             seg_detect<R>(a, rot.go_cur, slot_rep(s) * a.faces_per_replica, sm.cell[s][tid], v, j, sm.cand[tid],
                           sm.go_word(s, tid, a.go_k_cur), own, d_car, lead, d_light);
         }
@@ -1218,17 +1257,19 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
         issue_dyn(i + stride, s ^ 1);       // pending: GL(k), G2(k+1)
         cp_async_wait<1>();                 // GL(k) landed
         if (live)
-            seg_move<R, AUX, ENS>(a, rot, sm.logtab, i, 0, v, d_car, lead, d_light, own,
+            seg_move<R, AUX, ENS>(a, rot, sm.logtab, ic, 0, v, d_car, lead, d_light, own,
                                   [&](int rec, int ii, int sec) {
                                       if (ii > sec) return;
                                       pend_old = atomicMin(tab_next + (size_t)(uint32_t)rec * 8u, ii);
                                       pend_rec = rec;
+                                      if constexpr (ENS) sm.pend_car[tid] = ii;
                                   });
         cp_async_wait<0>();                 // G2(k+1) landed
         issue_cand_early_late(i + stride, s ^ 1, i + 2 * stride, s);   // pending: G3(k+1), G1(k+2), GL(k+1)
     }
     finish_insert(i - stride);
     cp_async_wait<0>();
+#undef n_walk
 }
 
 // ---------------------------------------------------------------------------------------------------------------
