@@ -304,9 +304,9 @@ def main():
                     help="c4_city_1m | c3_sf_50k | c2_manhattan_2k: one simulation per GPU")
     ap.add_argument("--replicas", type=int, default=4096, help="ensemble block: total number of rollouts (BASELINE configs[4])")
     ap.add_argument("--ensemble-max-steps", type=int, default=3000,
-                    help="ensemble block: rollout cap.  SURVEY c5 names 20,000 (3.1 s on one GPU, 4,076 of 4,096 agents arrive); "
-                         "after ~3,000 steps a few hundred replicas are left and a step is mostly the walk over frozen "
-                         "tiles, so the default measures the part of the sweep that exercises the kernel")
+                    help="ensemble block: rollout cap.  SURVEY c5 names 20,000 (1.75 s on one GPU, 4,076 of 4,096 agents arrive); "
+                         "after ~3,000 steps a few hundred replicas are left and a step shrinks towards the launch "
+                         "floor, so the default measures the part of the sweep that exercises the kernel")
     ap.add_argument("--agent", type=int, default=-1, help="ensemble block: agent car (-1: ensemble.pick_agent; learn.py uses 17)")
     ap.add_argument("--neighbor", default="atomic", choices=["atomic", "sort"],
                     help="how the per-bin leader table is built: atomicMin at the kernel tail (default) or the radix-sort "
