@@ -148,7 +148,8 @@ int tb2_step(tb2_sim* sim, double dt, int32_t n_steps, int32_t order, void* stre
  * terminate).  Small ensembles: one launch, each replica is one thread-block cluster whose world
  * stays on chip and which leaves the launch when its agent has arrived.  Large ensembles: batched per-step launches of
  * the HBM-streaming kernels; the cars of an arrived replica are no longer loaded or stepped, the done flags are read
- * back every 256 steps to stop as soon as every rollout is over.  A replica that has arrived stays frozen in later
+ * back every 256 steps - to stop as soon as every rollout is over, and to hand the kernel the list of the replicas still
+ * running so that it walks only their cars.  A replica that has arrived stays frozen in later
  * tb2_rollout calls; the state of its cars is the one of the arrival step (Env.step has returned, environment.py:124)
  * and is not meant to be stepped further with tb2_step.  Results: TB2_DONE / TB2_TRIP_TIME / TB2_TRIP_STEP. */
 int tb2_rollout(tb2_sim* sim, double dt, int32_t max_steps, int32_t order, void* stream);
