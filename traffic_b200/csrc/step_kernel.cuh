@@ -1087,6 +1087,7 @@ __global__ void TB2_PIPE_BOUNDS pipe_kernel(const __grid_constant__ StepArgsT<R>
                     r = sm.rep_next[tid]; c = sm.c_next[tid]; fz = a.freeze_done && sm.done_next[tid] != 0;
                 }
                 ii = r * a.cars_per_replica + c;
+                TB2_BOUNDS(r >= 0 && r < a.n_replicas && c >= 0 && c < a.cars_per_replica, 9);
             }
             sm.rep[s][tid] = fz ? -1 : r;
             sm.idx[s][tid] = ii;
